@@ -1,0 +1,532 @@
+// zf_capi.cu -- C ABI of the encode engine: encoder handle, batch submit/collect, device-resident
+// entry, the per-frame writeFrame mirror.  Declared in include/zigflac_b200.h.
+//
+// The reference's Encoder.writeFrame (encoder.zig:234) is synchronous and per frame; a GPU needs many
+// frames in flight, so the boundary is a batch: K frames of raw PCM in, K frames + K sizes out.
+// writeFrame is the K = 1 case (zf_write_frame).  No CPU fallback exists anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/zigflac_b200.h"
+#include "zf_kernel.cuh"
+#include "zf_kernel_indep.cuh"
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+#define ZF_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                     __LINE__);                                                                    \
+            return ZF_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+constexpr int kPow8Len = 1 << 18;  // covers the largest frame of the multi-channel path (8 ch x 4096 x 33 bits)
+
+struct Slot {  // one in-flight batch: device buffers + pinned staging
+    uint8_t *d_pcm = nullptr;
+    uint8_t *d_out = nullptr;
+    uint8_t *h_pcm = nullptr;   // pinned
+    uint8_t *h_out = nullptr;   // pinned
+    uint32_t *d_sizes = nullptr;
+    uint32_t *h_sizes = nullptr;  // pinned
+    unsigned long long *d_desc = nullptr;
+    unsigned int *d_ctl = nullptr;          // [0],[1] tickets, [2] status
+    unsigned long long *d_total = nullptr;
+    unsigned long long *h_total = nullptr;  // pinned: [0] total, [1] status
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    size_t pcm_cap = 0, out_cap = 0;
+    uint32_t frames = 0;  // frames of the batch in flight
+    bool busy = false;
+    bool have_io = false;
+};
+
+}  // namespace
+
+struct zf_encoder {
+    zf_config cfg;
+    int sm_count = 0;
+    int launches_last = 0;
+    float kernel_ms_last = 0.f;
+    uint16_t *d_pow8 = nullptr;
+    Slot slot[2];
+    int next_slot = 0;  // submit/collect use slot 0 only; zf_encode_pcm ping-pongs
+    size_t frame_pcm_bytes = 0;
+    size_t max_frame_bytes = 0;
+    bool stereo = false;
+    int occ_full = 0, occ_gen = 0;
+    size_t smem_stereo = 0;
+    size_t smem_indep = 0;
+};
+
+namespace {
+
+bool depth_ok(unsigned d) { return d == 16 || d == 24 || d == 32; }
+
+size_t max_frame_bytes_of(const zf_config *cfg) {
+    // encoder.zig:583-595 with the reference's own call-site quirk (:59 passes compute_waste_bits = true)
+    const size_t header_max = 2 + 7 + 2 + 2 + 1, subframe_header_max = 8, footer = 2;
+    const size_t bps = (cfg->channels == 2) ? (size_t)cfg->bit_depth + 1 : cfg->bit_depth;
+    const size_t byte_per_sample = (bps + 7) / 8;
+    return header_max + subframe_header_max * cfg->channels + (size_t)cfg->block_size * byte_per_sample * (cfg->channels + 1u) +
+           footer;
+}
+
+template <int BYTES, bool FULL>
+int setup_stereo_kernel(zf_encoder *e, int *occ) {
+    auto k = zf::zf_encode_stereo_kernel<BYTES, FULL>;
+    const size_t smem = sizeof(zf::SmemStereo<BYTES>);
+    ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, zf::kThreads, smem));
+    e->smem_stereo = smem;
+    return ZF_OK;
+}
+
+template <int BYTES>
+int setup_indep_kernel(zf_encoder *e, int *occ) {
+    auto k = zf::zf_encode_indep_kernel<BYTES>;
+    const size_t smem = zf::indep_smem_bytes(BYTES, e->cfg.channels);
+    ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, zf::kThreads, smem));
+    e->smem_indep = smem;
+    return ZF_OK;
+}
+
+int setup_kernels(zf_encoder *e) {
+    const int bytes = e->cfg.bit_depth / 8;
+    int rc = ZF_OK;
+    if (e->stereo) {
+        if (bytes == 2) { rc = setup_stereo_kernel<2, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<2, false>(e, &e->occ_gen); }
+        else if (bytes == 3) { rc = setup_stereo_kernel<3, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<3, false>(e, &e->occ_gen); }
+        else { rc = setup_stereo_kernel<4, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<4, false>(e, &e->occ_gen); }
+    } else {
+        if (bytes == 2) rc = setup_indep_kernel<2>(e, &e->occ_gen);
+        else if (bytes == 3) rc = setup_indep_kernel<3>(e, &e->occ_gen);
+        else rc = setup_indep_kernel<4>(e, &e->occ_gen);
+        e->occ_full = e->occ_gen;
+    }
+    if (rc) return rc;
+    if (e->occ_full < 1 || e->occ_gen < 1) {
+        snprintf(g_cuda_err, sizeof g_cuda_err, "kernel does not fit on an SM (occupancy 0)");
+        return ZF_ERR_CUDA;
+    }
+    return ZF_OK;
+}
+
+template <int BYTES>
+void launch_stereo(bool full, int grid, size_t smem, cudaStream_t s, const zf::FrameJob &job) {
+    if (full) zf::zf_encode_stereo_kernel<BYTES, true><<<grid, zf::kThreads, smem, s>>>(job);
+    else zf::zf_encode_stereo_kernel<BYTES, false><<<grid, zf::kThreads, smem, s>>>(job);
+}
+
+void launch_one(zf_encoder *e, bool full, int grid, cudaStream_t s, const zf::FrameJob &job) {
+    const int bytes = e->cfg.bit_depth / 8;
+    if (e->stereo) {
+        if (bytes == 2) launch_stereo<2>(full, grid, e->smem_stereo, s, job);
+        else if (bytes == 3) launch_stereo<3>(full, grid, e->smem_stereo, s, job);
+        else launch_stereo<4>(full, grid, e->smem_stereo, s, job);
+    } else {
+        if (bytes == 2) zf::zf_encode_indep_kernel<2><<<grid, zf::kThreads, e->smem_indep, s>>>(job);
+        else if (bytes == 3) zf::zf_encode_indep_kernel<3><<<grid, zf::kThreads, e->smem_indep, s>>>(job);
+        else zf::zf_encode_indep_kernel<4><<<grid, zf::kThreads, e->smem_indep, s>>>(job);
+    }
+}
+
+// Enqueue the kernels of one batch on `s`.  All pointers are device pointers.
+int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples, uint64_t first_frame_number, uint8_t *d_out,
+                 size_t out_cap, uint32_t *d_sizes, unsigned long long *d_total, cudaStream_t s, int *launches) {
+    const uint32_t bs = e->cfg.block_size;
+    const uint64_t frames = (samples + bs - 1) / bs;
+    const uint64_t full = samples / bs;
+    const uint32_t tail = (uint32_t)(samples - full * bs);
+    *launches = 0;
+    if (frames == 0) {
+        ZF_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s));
+        return ZF_OK;
+    }
+    if (frames > e->cfg.max_frames_per_batch) return ZF_ERR_INVALID_ARG;
+    if (first_frame_number + frames > (1ull << 31)) return ZF_ERR_UNSUPPORTED;  // header coder is UB upstream (Q16)
+    ZF_CUDA(cudaMemsetAsync(sl.d_desc, 0, sizeof(unsigned long long) * frames, s));
+    ZF_CUDA(cudaMemsetAsync(sl.d_ctl, 0, sizeof(unsigned int) * 4, s));
+    ZF_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s));
+    zf::FrameJob job;
+    memset(&job, 0, sizeof job);
+    job.out = d_out;
+    job.out_cap = out_cap;
+    job.frame_sizes = d_sizes;
+    job.desc = sl.d_desc;
+    job.status = sl.d_ctl + 2;
+    job.total_bytes = d_total;
+    job.pow8 = e->d_pow8;
+    job.batch_frames = (uint32_t)frames;
+    job.first_frame_number = first_frame_number;
+    job.frame_stride = (uint32_t)e->frame_pcm_bytes;
+    job.sample_rate = e->cfg.sample_rate;
+    job.channels = e->cfg.channels;
+    job.max_rice_order = e->cfg.max_rice_order;
+    job.max_rice_param = e->cfg.max_rice_param;
+    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock;
+    // the 1-D TMA bulk copy needs 16-byte aligned sources; frame strides are multiples of 16 already
+    job.use_tma = ((uintptr_t)d_pcm & 15u) == 0 ? 1u : 0u;
+    if (full) {
+        job.pcm = d_pcm;
+        job.n_frames = (uint32_t)full;
+        job.frame_base = 0;
+        job.block_size = bs;
+        job.ticket = sl.d_ctl + 0;
+        const int occ = fast ? e->occ_full : e->occ_gen;
+        const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
+        launch_one(e, fast, grid, s, job);
+        (*launches)++;
+    }
+    if (tail) {  // the short last frame: same stream, so every earlier descriptor is final by the time it runs
+        job.pcm = d_pcm + full * e->frame_pcm_bytes;
+        job.n_frames = 1;
+        job.frame_base = (uint32_t)full;
+        job.block_size = tail;
+        job.ticket = sl.d_ctl + 1;
+        launch_one(e, false, 1, s, job);
+        (*launches)++;
+    }
+    ZF_CUDA(cudaGetLastError());
+    return ZF_OK;
+}
+
+int ensure_io(zf_encoder *e, Slot &sl) {
+    if (sl.have_io) return ZF_OK;
+    const size_t frames = e->cfg.max_frames_per_batch;
+    sl.pcm_cap = frames * e->frame_pcm_bytes;
+    sl.out_cap = frames * e->max_frame_bytes + 64;
+    ZF_CUDA(cudaMalloc(&sl.d_pcm, sl.pcm_cap));
+    ZF_CUDA(cudaMalloc(&sl.d_out, sl.out_cap));
+    ZF_CUDA(cudaMallocHost(&sl.h_pcm, sl.pcm_cap));
+    ZF_CUDA(cudaMallocHost(&sl.h_out, sl.out_cap));
+    sl.have_io = true;
+    return ZF_OK;
+}
+
+int slot_init(zf_encoder *e, Slot &sl) {
+    const size_t frames = e->cfg.max_frames_per_batch;
+    ZF_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    ZF_CUDA(cudaEventCreate(&sl.ev_start));
+    ZF_CUDA(cudaEventCreate(&sl.ev_stop));
+    ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    ZF_CUDA(cudaMalloc(&sl.d_sizes, sizeof(uint32_t) * frames));
+    ZF_CUDA(cudaMalloc(&sl.d_desc, sizeof(unsigned long long) * frames));
+    ZF_CUDA(cudaMalloc(&sl.d_ctl, sizeof(unsigned int) * 4));
+    ZF_CUDA(cudaMalloc(&sl.d_total, sizeof(unsigned long long)));
+    ZF_CUDA(cudaMallocHost(&sl.h_sizes, sizeof(uint32_t) * frames));
+    ZF_CUDA(cudaMallocHost(&sl.h_total, sizeof(unsigned long long) * 2));
+    return ZF_OK;
+}
+
+void slot_free(Slot &sl) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    cudaFree(sl.d_pcm); cudaFree(sl.d_out); cudaFree(sl.d_sizes); cudaFree(sl.d_desc); cudaFree(sl.d_ctl); cudaFree(sl.d_total);
+    cudaFreeHost(sl.h_pcm); cudaFreeHost(sl.h_out); cudaFreeHost(sl.h_sizes); cudaFreeHost(sl.h_total);
+    if (sl.ev_start) cudaEventDestroy(sl.ev_start);
+    if (sl.ev_stop) cudaEventDestroy(sl.ev_stop);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+    sl = Slot();
+}
+
+bool is_pinned_or_device_visible(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// H2D + kernels + D2H of the small results for one batch held in a slot (asynchronous).
+int slot_submit(zf_encoder *e, Slot &sl, const uint8_t *pcm, uint64_t samples, uint64_t first_frame_number) {
+    int rc = ensure_io(e, sl);
+    if (rc) return rc;
+    const uint32_t bs = e->cfg.block_size;
+    const uint64_t frames = (samples + bs - 1) / bs;
+    if (frames > e->cfg.max_frames_per_batch) return ZF_ERR_INVALID_ARG;
+    const size_t bytes = (size_t)samples * e->cfg.channels * (e->cfg.bit_depth / 8);
+    const uint8_t *src = pcm;
+    if (bytes && !is_pinned_or_device_visible(pcm)) {  // pageable caller memory: stage through pinned
+        memcpy(sl.h_pcm, pcm, bytes);
+        src = sl.h_pcm;
+    }
+    if (bytes) ZF_CUDA(cudaMemcpyAsync(sl.d_pcm, src, bytes, cudaMemcpyHostToDevice, sl.stream));
+    ZF_CUDA(cudaEventRecord(sl.ev_start, sl.stream));
+    int launches = 0;
+    rc = launch_batch(e, sl, sl.d_pcm, samples, first_frame_number, sl.d_out, sl.out_cap, sl.d_sizes, sl.d_total, sl.stream,
+                      &launches);
+    if (rc) return rc;
+    ZF_CUDA(cudaEventRecord(sl.ev_stop, sl.stream));
+    e->launches_last = launches;
+    if (frames) ZF_CUDA(cudaMemcpyAsync(sl.h_sizes, sl.d_sizes, sizeof(uint32_t) * frames, cudaMemcpyDeviceToHost, sl.stream));
+    ZF_CUDA(cudaMemcpyAsync(sl.h_total, sl.d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.stream));
+    ZF_CUDA(cudaMemcpyAsync(sl.h_total + 1, sl.d_ctl + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, sl.stream));
+    ZF_CUDA(cudaEventRecord(sl.ev_done, sl.stream));
+    sl.frames = (uint32_t)frames;
+    sl.busy = true;
+    return ZF_OK;
+}
+
+// Wait for the batch, then bring exactly the produced bytes back.
+int slot_collect(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *out_len, uint32_t *frame_sizes,
+                 uint32_t frame_sizes_cap, uint32_t *n_frames) {
+    if (!sl.busy) return ZF_ERR_INVALID_ARG;
+    sl.busy = false;
+    ZF_CUDA(cudaEventSynchronize(sl.ev_done));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_stop) == cudaSuccess) e->kernel_ms_last = ms;
+    const unsigned int status = (unsigned int)sl.h_total[1];
+    if (status & zf::kStatusOutOverflow) return ZF_ERR_OUT_TOO_SMALL;
+    if (status) {
+        snprintf(g_cuda_err, sizeof g_cuda_err, "kernel status flags 0x%x", status);
+        return ZF_ERR_CUDA;
+    }
+    const size_t total = (size_t)sl.h_total[0];
+    if (n_frames) *n_frames = sl.frames;
+    if (out_len) *out_len = total;
+    if (sl.frames > frame_sizes_cap) return ZF_ERR_OUT_TOO_SMALL;
+    if (total > out_cap) return ZF_ERR_OUT_TOO_SMALL;
+    if (frame_sizes) memcpy(frame_sizes, sl.h_sizes, sizeof(uint32_t) * sl.frames);
+    if (total) {
+        if (is_pinned_or_device_visible(out)) {
+            ZF_CUDA(cudaMemcpyAsync(out, sl.d_out, total, cudaMemcpyDeviceToHost, sl.stream));
+            ZF_CUDA(cudaStreamSynchronize(sl.stream));
+        } else {
+            ZF_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, sl.stream));
+            ZF_CUDA(cudaStreamSynchronize(sl.stream));
+            memcpy(out, sl.h_out, total);
+        }
+    }
+    return ZF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *zf_last_cuda_error(void) { return g_cuda_err; }
+
+int zf_device_check(int device_id) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        snprintf(g_cuda_err, sizeof g_cuda_err, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return ZF_ERR_NO_DEVICE;
+    }
+    if (device_id < 0 || device_id >= n) return ZF_ERR_NO_DEVICE;
+    cudaDeviceProp p;
+    ZF_CUDA(cudaGetDeviceProperties(&p, device_id));
+    if (p.major != 10) {
+        snprintf(g_cuda_err, sizeof g_cuda_err, "device %d is sm_%d%d; this library carries sm_100a code only", device_id,
+                 p.major, p.minor);
+        return ZF_ERR_NO_DEVICE;
+    }
+    return ZF_OK;
+}
+
+int zf_config_default(zf_config *cfg, uint8_t channels, uint8_t bit_depth, uint32_t sample_rate) {
+    if (!cfg) return ZF_ERR_INVALID_ARG;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = sizeof *cfg;
+    cfg->block_size = 4096;  // encoder.zig:644
+    cfg->bit_depth = bit_depth;
+    cfg->channels = channels;
+    cfg->sample_rate = sample_rate;
+    cfg->stereo_decorrelation = 1;  // :649
+    cfg->max_rice_order = 8;        // :651
+    cfg->max_rice_param = 30;       // rice.MAX_PARAM, rice.zig:9-10
+    cfg->device_id = 0;
+    cfg->max_frames_per_batch = 2048;
+    return ZF_OK;
+}
+
+size_t zf_max_frame_bytes(const zf_config *cfg) { return cfg ? max_frame_bytes_of(cfg) : 0; }
+
+size_t zf_max_batch_bytes(const zf_config *cfg, uint32_t n_frames) {
+    return cfg ? (size_t)n_frames * max_frame_bytes_of(cfg) + 64 : 0;
+}
+
+int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
+    if (!cfg || !out) return ZF_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(zf_config)) return ZF_ERR_INVALID_ARG;
+    // asserts of Encoder.init, encoder.zig:49-51
+    if (cfg->block_size == 0 || cfg->channels == 0 || cfg->channels > 8 || cfg->bit_depth == 0 || cfg->bit_depth % 4 != 0)
+        return ZF_ERR_INVALID_ARG;
+    if (!depth_ok(cfg->bit_depth)) return ZF_ERR_UNSUPPORTED;          // 4/8/12/20-bit: unreachable upstream
+    if (cfg->block_size > zf::kMaxBlock) return ZF_ERR_UNSUPPORTED;    // one CTA holds at most 4096 samples/channel
+    if (cfg->max_rice_order > 8) return ZF_ERR_UNSUPPORTED;            // rice.MAX_ORDER = 8 (rice.zig:12)
+    if (cfg->max_rice_param == 0 || cfg->max_rice_param > 30) return ZF_ERR_UNSUPPORTED;  // 0: overflow upstream
+    if (cfg->max_frames_per_batch == 0) return ZF_ERR_INVALID_ARG;
+    int rc = zf_device_check(cfg->device_id);
+    if (rc) return rc;
+    ZF_CUDA(cudaSetDevice(cfg->device_id));
+    zf_encoder *e = new (std::nothrow) zf_encoder();
+    if (!e) return ZF_ERR_NOMEM;
+    e->cfg = *cfg;
+    e->stereo = cfg->channels == 2 && cfg->stereo_decorrelation;
+    e->frame_pcm_bytes = (size_t)cfg->block_size * cfg->channels * (cfg->bit_depth / 8);
+    e->max_frame_bytes = max_frame_bytes_of(cfg);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device_id) != cudaSuccess) { delete e; return ZF_ERR_CUDA; }
+    e->sm_count = prop.multiProcessorCount;
+    rc = setup_kernels(e);
+    if (!rc) rc = slot_init(e, e->slot[0]);
+    if (!rc) rc = slot_init(e, e->slot[1]);
+    if (!rc) {
+        std::vector<uint16_t> pw(kPow8Len);
+        uint32_t v = 1;
+        for (int k = 0; k < kPow8Len; k++) {
+            pw[k] = (uint16_t)v;
+            for (int b = 0; b < 8; b++) v = (v & 0x8000u) ? (((v << 1) ^ 0x8005u) & 0xffffu) : ((v << 1) & 0xffffu);
+        }
+        cudaError_t ce = cudaMalloc(&e->d_pow8, sizeof(uint16_t) * kPow8Len);
+        if (ce == cudaSuccess) ce = cudaMemcpy(e->d_pow8, pw.data(), sizeof(uint16_t) * kPow8Len, cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) {
+            snprintf(g_cuda_err, sizeof g_cuda_err, "pow8 table: %s", cudaGetErrorString(ce));
+            rc = ZF_ERR_CUDA;
+        }
+    }
+    if (rc) {
+        zf_encoder_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return ZF_OK;
+}
+
+void zf_encoder_destroy(zf_encoder *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device_id);
+    slot_free(e->slot[0]);
+    slot_free(e->slot[1]);
+    cudaFree(e->d_pow8);
+    delete e;
+}
+
+int zf_encode_submit(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channel, uint64_t first_frame_number) {
+    if (!e || (!pcm && samples_per_channel)) return ZF_ERR_INVALID_ARG;
+    if (e->slot[0].busy) return ZF_ERR_BUSY;
+    ZF_CUDA(cudaSetDevice(e->cfg.device_id));
+    return slot_submit(e, e->slot[0], pcm, samples_per_channel, first_frame_number);
+}
+
+int zf_encode_collect(zf_encoder *e, uint8_t *out, size_t out_cap, size_t *out_len, uint32_t *frame_sizes,
+                      uint32_t frame_sizes_cap, uint32_t *n_frames) {
+    if (!e || !out) return ZF_ERR_INVALID_ARG;
+    ZF_CUDA(cudaSetDevice(e->cfg.device_id));
+    return slot_collect(e, e->slot[0], out, out_cap, out_len, frame_sizes, frame_sizes_cap, n_frames);
+}
+
+int zf_encode_pcm(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channel, uint64_t first_frame_number, uint8_t *out,
+                  size_t out_cap, size_t *out_len, uint32_t *frame_sizes, uint32_t frame_sizes_cap, uint32_t *n_frames) {
+    if (!e || !out || (!pcm && samples_per_channel)) return ZF_ERR_INVALID_ARG;
+    if (e->slot[0].busy || e->slot[1].busy) return ZF_ERR_BUSY;
+    ZF_CUDA(cudaSetDevice(e->cfg.device_id));
+    const uint32_t bs = e->cfg.block_size;
+    const uint64_t frames = (samples_per_channel + bs - 1) / bs;
+    if (n_frames) *n_frames = (uint32_t)frames;
+    if (out_len) *out_len = 0;
+    if (frames > frame_sizes_cap && frame_sizes) return ZF_ERR_OUT_TOO_SMALL;
+    const uint64_t per = e->cfg.max_frames_per_batch;
+    const uint64_t nbatch = (frames + per - 1) / per;
+    const size_t ic_bytes = (size_t)e->cfg.channels * (e->cfg.bit_depth / 8);
+    size_t pos = 0;
+    float ms = 0.f;
+    int launches = 0;
+    // two slots ping-pong: batch i+1 uploads and encodes while batch i drains
+    for (uint64_t b = 0; b <= nbatch; b++) {
+        if (b < nbatch) {
+            const uint64_t f0 = b * per;
+            const uint64_t s0 = f0 * bs;
+            const uint64_t ns = std::min<uint64_t>(per * bs, samples_per_channel - s0);
+            int rc = slot_submit(e, e->slot[b & 1], pcm + s0 * ic_bytes, ns, first_frame_number + f0);
+            if (rc) { e->slot[0].busy = e->slot[1].busy = false; cudaDeviceSynchronize(); return rc; }
+            launches += e->launches_last;
+        }
+        if (b >= 1) {
+            const uint64_t f0 = (b - 1) * per;
+            size_t got = 0;
+            uint32_t nf = 0;
+            int rc = slot_collect(e, e->slot[(b - 1) & 1], out + pos, out_cap - pos, &got,
+                                  frame_sizes ? frame_sizes + f0 : nullptr, frame_sizes ? (uint32_t)(frames - f0) : 0xffffffffu,
+                                  &nf);
+            if (rc) { e->slot[0].busy = e->slot[1].busy = false; cudaDeviceSynchronize(); return rc; }
+            pos += got;
+            ms += e->kernel_ms_last;
+        }
+    }
+    e->kernel_ms_last = ms;
+    e->launches_last = launches;
+    if (out_len) *out_len = pos;
+    return ZF_OK;
+}
+
+int zf_encode_device(zf_encoder *e, const void *d_pcm, uint64_t samples_per_channel, uint64_t first_frame_number, void *d_out,
+                     size_t out_cap, uint32_t *d_frame_sizes, uint64_t *d_total_bytes, void *stream) {
+    if (!e || !d_out || !d_frame_sizes || !d_total_bytes || (!d_pcm && samples_per_channel)) return ZF_ERR_INVALID_ARG;
+    ZF_CUDA(cudaSetDevice(e->cfg.device_id));
+    Slot &sl = e->slot[0];
+    cudaStream_t s = stream ? (cudaStream_t)stream : sl.stream;
+    ZF_CUDA(cudaEventRecord(sl.ev_start, s));
+    int launches = 0;
+    int rc = launch_batch(e, sl, (const uint8_t *)d_pcm, samples_per_channel, first_frame_number, (uint8_t *)d_out, out_cap,
+                          d_frame_sizes, (unsigned long long *)d_total_bytes, s, &launches);
+    if (rc) return rc;
+    ZF_CUDA(cudaEventRecord(sl.ev_stop, s));
+    e->launches_last = launches;
+    return ZF_OK;
+}
+
+int zf_last_batch_stats(zf_encoder *e, float *kernel_ms, uint32_t *launches) {
+    if (!e) return ZF_ERR_INVALID_ARG;
+    Slot &sl = e->slot[0];
+    if (kernel_ms) {
+        // valid for the device-resident path once its stream has been synchronised; the host path caches its own
+        float ms = 0.f;
+        if (cudaEventQuery(sl.ev_stop) == cudaSuccess && cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_stop) == cudaSuccess)
+            e->kernel_ms_last = std::max(e->kernel_ms_last, 0.f), *kernel_ms = (e->slot[0].busy ? e->kernel_ms_last : ms);
+        else *kernel_ms = e->kernel_ms_last;
+        cudaGetLastError();
+    }
+    if (launches) *launches = (uint32_t)e->launches_last;
+    return ZF_OK;
+}
+
+int zf_write_frame(zf_encoder *e, const int32_t *const *planes, uint32_t samples_count, uint64_t frame_number, uint8_t *out,
+                   size_t out_cap, size_t *frame_len) {
+    if (!e || !planes || !out || samples_count == 0) return ZF_ERR_INVALID_ARG;  // assert encoder.zig:235
+    if (samples_count > e->cfg.block_size) return ZF_ERR_INVALID_ARG;
+    // planar sign-extended i32 (Encoder.samples) -> the packed interleaved layout the kernels unpack
+    const unsigned ch = e->cfg.channels, nb = e->cfg.bit_depth / 8;
+    std::vector<uint8_t> pcm((size_t)samples_count * ch * nb);
+    size_t o = 0;
+    for (uint32_t i = 0; i < samples_count; i++)
+        for (unsigned c = 0; c < ch; c++) {
+            const uint32_t v = (uint32_t)planes[c][i];
+            for (unsigned k = 0; k < nb; k++) pcm[o++] = (uint8_t)(v >> (8 * k));
+        }
+    uint32_t size = 0, nf = 0;
+    size_t len = 0;
+    int rc = zf_encode_pcm(e, pcm.data(), samples_count, frame_number, out, out_cap, &len, &size, 1, &nf);
+    if (rc) return rc;
+    if (frame_len) *frame_len = len;
+    return ZF_OK;
+}
+
+}  // extern "C"
