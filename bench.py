@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- FLAC encode throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of the encode hot path over the whole synthetic stream of the named config
+(BASELINE.json configs[1]: 24-bit stereo 96 kHz, 10 min = 57.6 M samples/channel, 14 063 frames of
+4096, reference Config.default).  With N > 1 ranks (torchrun) the stream is N x 10 min and every
+rank encodes one contiguous frame range on its own GPU ("weak" scaling; no data-path collective --
+frames are independent).  `value` is device-resident whole-job MSamples/s (samples x channels);
+`e2e` is the same metric through the C-ABI call with pinned HOST buffers (H2D + encode + D2H in the
+timed region).  `--impl reference` times the CPU restatement of the reference (oracle port: the
+reference is Zig and cannot be built here) on all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (bit_depth, sample_rate, seconds)
+    "c1_16bit_44k1_60s": (16, 44100, 60),
+    "c2_24bit_96k_600s": (24, 96000, 600),
+    "c3_32bit_192k_600s": (32, 192000, 600),
+}
+DEFAULT_WORKLOAD = "c2_24bit_96k_600s"
+BLOCK = 4096
+CHANNELS = 2
+METRIC = "encode_msamples_per_s"
+UNIT = "MSamples/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="device-resident steps only (for runs under ncu)")
+    return ap.parse_args()
+
+
+def shard_of(total_samples, world, rank):
+    """Contiguous frame ranges: rank g gets frames [g*ceil(F/G), ...)."""
+    frames = (total_samples + BLOCK - 1) // BLOCK
+    per = (frames + world - 1) // world
+    f0 = min(per * rank, frames)
+    f1 = min(f0 + per, frames)
+    s0 = f0 * BLOCK
+    s1 = min(f1 * BLOCK, total_samples)
+    return f0, f1 - f0, s0, max(s1 - s0, 0)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML, ~5 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.sm = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                r = get(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def load_ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for name in sorted(os.listdir(pdir)):
+            if name.endswith("_roofline.json"):
+                try:
+                    best = json.load(open(os.path.join(pdir, name)))
+                except Exception:
+                    pass
+    return best
+
+
+def measured_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path, restated (oracle port), all host threads."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib
+    import zigflac_b200 as zf
+    bits, rate, seconds = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    # bounded sample of the workload per step: sized for roughly 1-2 s of work on this host
+    sample_seconds = min(seconds, 60 if bits == 16 else 30)
+    n = (rate * sample_seconds // BLOCK) * BLOCK
+    pcm = zf.synth_pcm(n, rate, bits)
+    cfg = oracle_lib.config(CHANNELS, bits)
+    for _ in range(max(1, min(args.warmup, 2))):
+        oracle_lib.encode_pcm(pcm, n, cfg, rate, threads=cores)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out, sizes = oracle_lib.encode_pcm(pcm, n, cfg, rate, threads=cores)
+    dt = (time.perf_counter() - t0) / steps
+    value = n * CHANNELS / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload, "bit_depth": bits, "sample_rate": rate, "channels": CHANNELS,
+                   "block_size": BLOCK, "prediction": "fixed", "stereo_decorrelation": True, "max_rice_order": 8,
+                   "note": "reference is Zig (no toolchain here): C restatement of zig-flac (oracle port), frames sharded over host threads"},
+        "realtime_x": round(n / dt / rate, 1),
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"first {sample_seconds} s of the stream ({n} samples/channel) per step"},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import zigflac_b200 as zf
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the encode path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    bits, rate, seconds = WORKLOADS[args.workload]
+    total_samples = rate * seconds * world  # weak scaling: the stream grows with the rank count
+    f0, nframes, s0, nsamples = shard_of(total_samples, world, rank)
+    ic_bytes = CHANNELS * bits // 8
+    pcm_bytes = nsamples * ic_bytes
+
+    # synthetic PCM of this rank's shard -> pinned host memory -> HBM
+    h_pcm = torch.empty(pcm_bytes, dtype=torch.uint8, pin_memory=True)
+    threads = max(1, (os.cpu_count() or 1) // max(1, min(world, 8)))
+    zf.synth_pcm(nsamples, rate, bits, first_sample=s0, threads=threads, out=h_pcm.numpy())
+    d_pcm = h_pcm.to(dev, non_blocking=True)
+
+    enc = zf.Encoder(zf.Config.default(CHANNELS, bits), rate, device_id=local_rank,
+                     max_frames_per_batch=max(nframes, 1))
+    out_cap = enc.max_batch_bytes(nframes)
+    d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
+    d_sizes = torch.zeros(max(nframes, 1), dtype=torch.int32, device=dev)
+    d_total = torch.zeros(1, dtype=torch.int64, device=dev)
+    # a non-default stream: its handle is what the C ABI launches on, and the torch events below record on it
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.synchronize(dev)
+
+    def step():
+        enc.encode_device(d_pcm.data_ptr(), nsamples, f0, d_out.data_ptr(), out_cap, d_sizes.data_ptr(),
+                          d_total.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    enc.kernel_times()  # drop warm-up records
+    flac_bytes = int(d_total.item())
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    ms_total = ev0.elapsed_time(ev1)
+    ktimes = enc.kernel_times()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": round(ms_step, 4), "kernel_ms": ktimes}), flush=True)
+        enc.close()
+        return
+
+    # ---- end to end through the C ABI with pinned host buffers (H2D + encode + D2H every step) ----
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
+    enc2 = zf.Encoder(zf.Config.default(CHANNELS, bits), rate, device_id=local_rank, max_frames_per_batch=1024)
+    h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
+    h_out_np = h_out.numpy()
+    h_pcm_np = h_pcm.numpy()
+    got, sizes = enc2.encode_pcm(h_pcm_np, nsamples, f0, out=h_out_np)  # warm-up (allocates the staging slots)
+    enc2.encode_pcm(h_pcm_np, nsamples, f0, out=h_out_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        got, sizes = enc2.encode_pcm(h_pcm_np, nsamples, f0, out=h_out_np)
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_out_bytes = int(got.size) + 4 * int(sizes.size)
+
+    # the device-resident result and the host-path result are the same bytes
+    same = bool((d_out[:flac_bytes].cpu().numpy() == got).all()) and flac_bytes == int(got.size)
+
+    # totals over ranks
+    tot = torch.tensor([nsamples, flac_bytes, pcm_bytes, e2e_out_bytes], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    all_samples, all_flac, all_pcm, all_e2e_out = [int(v) for v in tot.tolist()]
+
+    if rank == 0:
+        value = all_samples * CHANNELS / (ms_step * 1e-3) / 1e6
+        e2e_value = all_samples * CHANNELS / e2e_s / 1e6
+        peak, peak_src = measured_peak()
+        k_ms = statistics.mean(ktimes) if ktimes else ms_step
+        full_frames = nsamples // BLOCK
+        # algorithmic bytes of one launch of the dominant kernel: packed PCM in + encoded frame bytes out
+        sizes_np = d_sizes[:nframes].cpu().numpy()
+        kernel_bytes = full_frames * BLOCK * ic_bytes + int(sizes_np[:full_frames].sum())
+        achieved = kernel_bytes / (k_ms * 1e-3) / 1e9
+        ncu = load_ncu_traffic()
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32" if bits < 32 else "int64", "data": "synthetic",
+            "config": {"workload": args.workload, "bit_depth": bits, "sample_rate": rate, "channels": CHANNELS,
+                       "block_size": BLOCK, "prediction": "fixed", "stereo_decorrelation": True, "max_rice_order": 8,
+                       "max_rice_param": 30, "seconds_per_gpu": seconds, "frames_per_gpu": nframes,
+                       "parallelism": f"frame-range shards x{world}, no collective",
+                       "l2": f"input {pcm_bytes / 1e6:.0f} MB + output {flac_bytes / 1e6:.0f} MB per GPU per step, larger than the 126 MB L2"},
+            "realtime_x": round(all_samples / (ms_step * 1e-3) / rate, 1),
+            "compression_ratio": round(all_flac / all_pcm, 4),
+            "clocks": sampler.summary(),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": all_pcm,
+                    "d2h_bytes_per_step": all_e2e_out, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
+                    "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 1024-frame batches, 2 slots)"},
+            "gpu_launches": args.steps * (1 + (1 if nsamples % BLOCK else 0)),
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
+                         "kernel": "zf_encode_stereo_kernel<3,true>" if bits == 24 else "zf_encode_stereo_kernel",
+                         "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": kernel_bytes,
+                         "peak_source": peak_src,
+                         "note": "integer-issue bound, not HBM bound: see DESIGN.md (about 150 integer ops per inter-channel sample)"},
+            "parity": {"device_path_equals_host_path": same},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_lib
+            sample_seconds = 120
+            n = (rate * sample_seconds // BLOCK) * BLOCK
+            cfg = oracle_lib.config(CHANNELS, bits)
+            sample = h_pcm_np[: n * ic_bytes]
+            t0 = time.perf_counter()
+            ref, ref_sizes = oracle_lib.encode_pcm(sample, n, cfg, rate, threads=1)
+            dt1 = time.perf_counter() - t0
+            cores = os.cpu_count() or 1
+            t0 = time.perf_counter()
+            oracle_lib.encode_pcm(sample, n, cfg, rate, threads=cores)
+            dtn = time.perf_counter() - t0
+            nb = int(ref_sizes.sum())
+            line["cpu_baseline"] = {
+                "value": round(n * CHANNELS / dt1 / 1e6, 2), "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"first {sample_seconds} s of the stream ({n} samples/channel), C restatement of zig-flac (the reference is single-threaded)",
+                "all_cores": {"value": round(n * CHANNELS / dtn / 1e6, 2), "cores": cores},
+            }
+            line["parity"]["gpu_equals_oracle_on_sample"] = bool(nb <= got.size and (got[:nb] == ref).all())
+        print(json.dumps(line), flush=True)
+    enc.close()
+    enc2.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

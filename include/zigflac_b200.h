@@ -117,6 +117,10 @@ int zf_write_frame(zf_encoder *enc, const int32_t *const *planes, uint32_t sampl
 /* Device time (ms, CUDA events on the launch stream) of the kernels of the last completed batch,
  * and how many kernel launches it took. */
 int zf_last_batch_stats(zf_encoder *enc, float *kernel_ms, uint32_t *launches);
+/* Device durations (ms, CUDA events on the launch stream) of the full-frame encode kernel of the batches
+ * enqueued since the previous call (at most 256 per slot are kept); waits for them to finish.  Used by
+ * bench.py for the roofline figure. */
+int zf_kernel_times(zf_encoder *enc, float *ms, uint32_t cap, uint32_t *n);
 
 const char *zf_strerror(int status);
 const char *zf_last_cuda_error(void);

@@ -1,0 +1,116 @@
+"""CPU test of the encode KERNELS' integer logic: zig-flac_b200/csrc/zf_kernel*.cuh compiled with
+-DZF_HOST_EMU (tests/kernel_emu: CUDA threads as fibers) and compared byte for byte with the oracle.
+
+This is a development/test harness for a box without a GPU.  It is not a product path and not a
+fallback: the test library is separate from libzigflac_b200.so, which fails without a CUDA device.
+The parity tests proper are tests/test_gpu_parity.py (-m gpu), through the C ABI on a B200.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import signals
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "kernel_emu")
+EMU_SO = os.path.join(EMU_DIR, "_build", "libzf_emu.so")
+CSRC = os.path.join(os.path.dirname(HERE), "zig-flac_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    srcs = [os.path.join(EMU_DIR, f) for f in ("emu_main.cpp", "cuda_emu.h")] + [
+        os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_dev.h")]
+    if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
+        os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", EMU_SO,
+                        os.path.join(EMU_DIR, "emu_main.cpp")], check=True)
+    lib = C.CDLL(EMU_SO)
+    lib.emu_encode.restype = C.c_longlong
+    lib.emu_encode.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_uint, C.c_int, C.c_uint, C.c_uint, C.c_ulonglong,
+                               C.c_uint, C.c_uint, C.c_void_p, C.c_ulonglong, C.c_void_p, C.POINTER(C.c_uint32)]
+    lib.emu_best_param.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)]
+    return lib
+
+
+def _emu_encode(emu, pcm, n, bits, channels=2, dec=1, block=4096, rate=44100, first=0, mro=8, mrp=30):
+    pcm = np.ascontiguousarray(pcm)
+    frames = (n + block - 1) // block
+    cap = frames * (channels + 1) * block * 5 + 4096
+    out = np.zeros(cap, dtype=np.uint8)
+    sizes = np.zeros(frames + 1, dtype=np.uint32)
+    nf = C.c_uint32()
+    tot = emu.emu_encode(pcm.ctypes.data, n, bits // 8, channels, dec, block, rate, first, mro, mrp, out.ctypes.data, cap,
+                         sizes.ctypes.data, C.byref(nf))
+    assert tot >= 0, tot
+    return out[:tot], sizes[:nf.value]
+
+
+def _check(emu, oracle, pcm, n, bits, **kw):
+    cfg = oracle.config(kw.get("channels", 2), bits, block_size=kw.get("block", 4096),
+                        stereo_decorrelation=kw.get("dec", 1), max_rice_order=kw.get("mro", 8),
+                        max_rice_param=kw.get("mrp", 30))
+    ref, rs = oracle.encode_pcm(pcm, n, cfg, kw.get("rate", 44100), kw.get("first", 0))
+    got, gs = _emu_encode(emu, pcm, n, bits, **kw)
+    assert np.array_equal(rs, gs)
+    assert ref.tobytes() == got.tobytes()
+
+
+def test_closed_form_parameter_search_equals_brute_force(emu, oracle):
+    """best_param() picks the same (choice, cost) as the reference's loop (rice.zig:359-379)."""
+    rng = np.random.default_rng(1)
+    f = oracle.lib().zo_flac_calc_part_size
+    for _ in range(20000):
+        n = int(rng.choice([0, 1, 2, 3, 12, 13, 15, 16, 32, 255, 256, 1000, 4092, 4096]))
+        S = int(rng.integers(0, 1 << int(rng.integers(1, 50))))
+        if rng.random() < 0.25:
+            S = int(rng.integers(0, 4 * n + 3))
+        B, P = int(rng.integers(0, 33)), int(rng.integers(1, 31))
+        best, ch = ((5 + B * n) if B <= 31 else (1 << 64) - 1), 0x80 | B
+        for p in range(P):
+            c = f(n, p, S)
+            if c < best:
+                best, ch = c, p
+        c_out, k_out = C.c_uint(), C.c_ulonglong()
+        emu.emu_best_param(S, B, n, P, C.byref(c_out), C.byref(k_out))
+        assert (c_out.value, k_out.value) == (ch, best), (S, B, n, P)
+
+
+@pytest.mark.parametrize("bits", [16, 24, 32])
+def test_stereo_kernel_logic_on_input_classes(emu, oracle, bits):
+    for name, L, R in signals.stereo_classes(bits, n=4096 + 333):
+        pcm = oracle.pcm_bytes_from_int(signals.interleave([L, R]), bits)
+        _check(emu, oracle, pcm, L.size, bits)
+
+
+def test_kernel_logic_short_frames_and_variants(emu, oracle):
+    rng = np.random.default_rng(9)
+    for bits in (16, 32):
+        F = 1 << (bits - 1)
+        for m in (1, 4, 5, 16, 17, 255, 256, 1000, 2048, 4080):
+            t = np.arange(m)
+            L = (0.3 * F * np.sin(t * 0.05)).astype(np.int64) + rng.integers(-3, 4, m)
+            pcm = oracle.pcm_bytes_from_int(signals.interleave([L, L // 2]), bits)
+            _check(emu, oracle, pcm, m, bits)
+        n = 4096 + 100
+        L = rng.integers(-F // 8, F // 8, n)
+        pcm = oracle.pcm_bytes_from_int(signals.interleave([L, L + rng.integers(-50, 50, n)]), bits)
+        for fn in (127, 2047, 65535, (1 << 26) + 5):
+            _check(emu, oracle, pcm, n, bits, first=fn)
+        for kw in ({"mro": 0}, {"mro": 5}, {"mrp": 1}, {"mrp": 15}, {"block": 576}, {"block": 1000}, {"rate": 11025},
+                   {"dec": 0}):
+            _check(emu, oracle, pcm, n, bits, **kw)
+
+
+@pytest.mark.parametrize("channels", [1, 3, 8])
+def test_independent_channel_kernel_logic(emu, oracle, channels):
+    rng = np.random.default_rng(channels)
+    for bits in (16, 24, 32):
+        F = 1 << (bits - 1)
+        n = 4096 + 77
+        planes = [rng.integers(-F // 4, F // 4, n) if c % 2 else np.cumsum(rng.integers(-9, 10, n)) for c in range(channels)]
+        pcm = oracle.pcm_bytes_from_int(signals.interleave(planes), bits)
+        _check(emu, oracle, pcm, n, bits, channels=channels, rate=48000)

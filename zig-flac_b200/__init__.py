@@ -100,6 +100,7 @@ def _lib():
     L.zf_encode_device.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_size_t, vp, vp, vp]
     L.zf_write_frame.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_uint64, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.zf_last_batch_stats.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
+    L.zf_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint32)]
     L.zf_streaminfo_init.argtypes = [C.POINTER(ZfStreamInfo)]
     L.zf_streaminfo_init.restype = None
     L.zf_streaminfo_update_frame_size.argtypes = [C.POINTER(ZfStreamInfo), C.c_uint32]
@@ -332,6 +333,19 @@ class Encoder:
         n = C.c_uint32()
         _lib().zf_last_batch_stats(self.handle, C.byref(ms), C.byref(n))
         return ms.value, n.value
+
+
+def _kernel_times(self, cap=512):
+    """Durations (ms) of the full-frame kernel launches since the previous call."""
+    buf = (C.c_float * cap)()
+    n = C.c_uint32()
+    rc = _lib().zf_kernel_times(self.handle, buf, cap, C.byref(n))
+    if rc != ZF_OK:
+        raise FlacGpuError(rc, "kernel_times")
+    return [buf[i] for i in range(n.value)]
+
+
+Encoder.kernel_times = _kernel_times
 
 
 def wav_to_flac(wav_bytes, devices=None):

@@ -31,7 +31,8 @@ thread_local char g_cuda_err[256] = "";
         }                                                                                          \
     } while (0)
 
-constexpr int kPow8Len = 1 << 18;  // covers the largest frame of the multi-channel path (8 ch x 4096 x 33 bits)
+constexpr int kPow8Len = 1 << 18;
+constexpr int kRing = 256;  // covers the largest frame of the multi-channel path (8 ch x 4096 x 33 bits)
 
 struct Slot {  // one in-flight batch: device buffers + pinned staging
     uint8_t *d_pcm = nullptr;
@@ -46,6 +47,8 @@ struct Slot {  // one in-flight batch: device buffers + pinned staging
     unsigned long long *h_total = nullptr;  // pinned: [0] total, [1] status
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    cudaEvent_t kev[2 * kRing] = {};  // start/stop pairs around the full-frame kernel of recent batches
+    uint32_t kev_count = 0;           // pairs recorded since the last zf_kernel_times()
     size_t pcm_cap = 0, out_cap = 0;
     uint32_t frames = 0;  // frames of the batch in flight
     bool busy = false;
@@ -187,7 +190,11 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         job.ticket = sl.d_ctl + 0;
         const int occ = fast ? e->occ_full : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
+        const uint32_t ring = sl.kev_count % kRing;
+        ZF_CUDA(cudaEventRecord(sl.kev[2 * ring], s));
         launch_one(e, fast, grid, s, job);
+        ZF_CUDA(cudaEventRecord(sl.kev[2 * ring + 1], s));
+        sl.kev_count++;
         (*launches)++;
     }
     if (tail) {  // the short last frame: same stream, so every earlier descriptor is final by the time it runs
@@ -222,6 +229,7 @@ int slot_init(zf_encoder *e, Slot &sl) {
     ZF_CUDA(cudaEventCreate(&sl.ev_start));
     ZF_CUDA(cudaEventCreate(&sl.ev_stop));
     ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    for (int i = 0; i < 2 * kRing; i++) ZF_CUDA(cudaEventCreate(&sl.kev[i]));
     ZF_CUDA(cudaMalloc(&sl.d_sizes, sizeof(uint32_t) * frames));
     ZF_CUDA(cudaMalloc(&sl.d_desc, sizeof(unsigned long long) * frames));
     ZF_CUDA(cudaMalloc(&sl.d_ctl, sizeof(unsigned int) * 4));
@@ -238,6 +246,7 @@ void slot_free(Slot &sl) {
     if (sl.ev_start) cudaEventDestroy(sl.ev_start);
     if (sl.ev_stop) cudaEventDestroy(sl.ev_stop);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    for (int i = 0; i < 2 * kRing; i++) if (sl.kev[i]) cudaEventDestroy(sl.kev[i]);
     if (sl.stream) cudaStreamDestroy(sl.stream);
     sl = Slot();
 }
@@ -495,16 +504,29 @@ int zf_encode_device(zf_encoder *e, const void *d_pcm, uint64_t samples_per_chan
 
 int zf_last_batch_stats(zf_encoder *e, float *kernel_ms, uint32_t *launches) {
     if (!e) return ZF_ERR_INVALID_ARG;
-    Slot &sl = e->slot[0];
-    if (kernel_ms) {
-        // valid for the device-resident path once its stream has been synchronised; the host path caches its own
-        float ms = 0.f;
-        if (cudaEventQuery(sl.ev_stop) == cudaSuccess && cudaEventElapsedTime(&ms, sl.ev_start, sl.ev_stop) == cudaSuccess)
-            e->kernel_ms_last = std::max(e->kernel_ms_last, 0.f), *kernel_ms = (e->slot[0].busy ? e->kernel_ms_last : ms);
-        else *kernel_ms = e->kernel_ms_last;
-        cudaGetLastError();
-    }
+    if (kernel_ms) *kernel_ms = e->kernel_ms_last;
     if (launches) *launches = (uint32_t)e->launches_last;
+    return ZF_OK;
+}
+
+int zf_kernel_times(zf_encoder *e, float *ms, uint32_t cap, uint32_t *n) {
+    if (!e || !n) return ZF_ERR_INVALID_ARG;
+    ZF_CUDA(cudaSetDevice(e->cfg.device_id));
+    uint32_t got = 0;
+    for (int si = 0; si < 2; si++) {
+        Slot &sl = e->slot[si];
+        const uint32_t have = std::min<uint32_t>(sl.kev_count, kRing);
+        for (uint32_t k = 0; k < have; k++) {
+            const uint32_t ring = (sl.kev_count - have + k) % kRing;
+            float v = 0.f;
+            ZF_CUDA(cudaEventSynchronize(sl.kev[2 * ring + 1]));
+            ZF_CUDA(cudaEventElapsedTime(&v, sl.kev[2 * ring], sl.kev[2 * ring + 1]));
+            if (ms && got < cap) ms[got] = v;
+            got++;
+        }
+        sl.kev_count = 0;
+    }
+    *n = got < cap ? got : cap;
     return ZF_OK;
 }
 
