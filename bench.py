@@ -255,6 +255,7 @@ def main():
     sampler.join()
     ms_total = ev0.elapsed_time(ev1)
     ktimes = enc.kernel_times()
+    launches_per_step = enc.last_batch_stats()[1]  # full-frame kernel (+ last-frame kernel + append when the stream ends short)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -321,7 +322,7 @@ def main():
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": all_pcm,
                     "d2h_bytes_per_step": all_e2e_out, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
                     "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 1024-frame batches, 2 slots)"},
-            "gpu_launches": args.steps * (1 + (1 if nsamples % BLOCK else 0)),
+            "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
                          "kernel": "zf_encode_stereo_kernel<3,true>" if bits == 24 else "zf_encode_stereo_kernel",

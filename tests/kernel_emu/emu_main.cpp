@@ -13,6 +13,7 @@ namespace zf { alignas(128) unsigned char zf_smem[256 * 1024]; }
 
 #include "../../zig-flac_b200/csrc/zf_kernel.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_indep.cuh"
+#include "../../zig-flac_b200/csrc/zf_kernel_full.cuh"
 
 namespace emu {
 emu_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
@@ -116,9 +117,15 @@ static void kernel_entry(void *) {
         else zf::zf_encode_indep_kernel<4>(g_job);
         return;
     }
-    if (g_bytes == 2) { if (g_full) zf::zf_encode_stereo_kernel<2, true>(g_job); else zf::zf_encode_stereo_kernel<2, false>(g_job); }
-    else if (g_bytes == 3) { if (g_full) zf::zf_encode_stereo_kernel<3, true>(g_job); else zf::zf_encode_stereo_kernel<3, false>(g_job); }
-    else { if (g_full) zf::zf_encode_stereo_kernel<4, true>(g_job); else zf::zf_encode_stereo_kernel<4, false>(g_job); }
+    if (g_full) {
+        if (g_bytes == 2) zf::zf_encode_stereo_full_kernel<2>(g_job);
+        else if (g_bytes == 3) zf::zf_encode_stereo_full_kernel<3>(g_job);
+        else zf::zf_encode_stereo_full_kernel<4>(g_job);
+        return;
+    }
+    if (g_bytes == 2) zf::zf_encode_stereo_kernel<2, false>(g_job);
+    else if (g_bytes == 3) zf::zf_encode_stereo_kernel<3, false>(g_job);
+    else zf::zf_encode_stereo_kernel<4, false>(g_job);
 }
 
 static uint16_t *make_pow8(int n) {
@@ -147,7 +154,7 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     unsigned ticket = 0, status = 0;
     unsigned long long total = 0;
     static uint16_t *pow8 = make_pow8(1 << 18);
-    emu::g_blockDim.x = 256;
+    emu::g_blockDim.x = zf::kThreads;
     emu::g_gridDim.x = 1;
     emu::g_blockIdx.x = 0;
     zf::FrameJob j;
@@ -160,17 +167,17 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     g_bytes = bytes_per_sample;
     if (full) {
         j.pcm = pcm; j.n_frames = (uint32_t)full; j.frame_base = 0; j.block_size = block_size;
-        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep;
+        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8;
         g_job = j;
         ticket = 0;
-        emu::run_block(kernel_entry, nullptr, 256);
+        emu::run_block(kernel_entry, nullptr, zf::kThreads);
     }
     if (tail) {
         j.pcm = pcm + full * j.frame_stride; j.n_frames = 1; j.frame_base = (uint32_t)full; j.block_size = tail;
         g_full = 0;
         g_job = j;
         ticket = 0;
-        emu::run_block(kernel_entry, nullptr, 256);
+        emu::run_block(kernel_entry, nullptr, zf::kThreads);
     }
     if (n_frames_out) *n_frames_out = (uint32_t)frames;
     if (status) return -(long long)status;

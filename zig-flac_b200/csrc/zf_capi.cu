@@ -16,6 +16,7 @@
 #include "../../include/zigflac_b200.h"
 #include "zf_kernel.cuh"
 #include "zf_kernel_indep.cuh"
+#include "zf_kernel_full.cuh"
 
 namespace {
 
@@ -46,6 +47,10 @@ struct Slot {  // one in-flight batch: device buffers + pinned staging
     unsigned long long *d_total = nullptr;
     unsigned long long *h_total = nullptr;  // pinned: [0] total, [1] status
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;              // the short last frame is encoded here, concurrently
+    cudaEvent_t ev_in = nullptr, ev_tail = nullptr;
+    uint8_t *d_tail = nullptr;               // private output of the last-frame launch
+    unsigned long long *d_tail_meta = nullptr;  // [0] desc, [1] total, [2] lo32: frame size
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
     cudaEvent_t kev[2 * kRing] = {};  // start/stop pairs around the full-frame kernel of recent batches
     uint32_t kev_count = 0;           // pairs recorded since the last zf_kernel_times()
@@ -88,7 +93,8 @@ size_t max_frame_bytes_of(const zf_config *cfg) {
 
 template <int BYTES, bool FULL>
 int setup_stereo_kernel(zf_encoder *e, int *occ) {
-    auto k = zf::zf_encode_stereo_kernel<BYTES, FULL>;
+    void (*k)(const zf::FrameJob) = zf::zf_encode_stereo_kernel<BYTES, false>;
+    if (FULL) k = zf::zf_encode_stereo_full_kernel<BYTES>;
     const size_t smem = sizeof(zf::SmemStereo<BYTES>);
     ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ZF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, zf::kThreads, smem));
@@ -129,7 +135,7 @@ int setup_kernels(zf_encoder *e) {
 
 template <int BYTES>
 void launch_stereo(bool full, int grid, size_t smem, cudaStream_t s, const zf::FrameJob &job) {
-    if (full) zf::zf_encode_stereo_kernel<BYTES, true><<<grid, zf::kThreads, smem, s>>>(job);
+    if (full) zf::zf_encode_stereo_full_kernel<BYTES><<<grid, zf::kThreads, smem, s>>>(job);
     else zf::zf_encode_stereo_kernel<BYTES, false><<<grid, zf::kThreads, smem, s>>>(job);
 }
 
@@ -179,15 +185,39 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     job.channels = e->cfg.channels;
     job.max_rice_order = e->cfg.max_rice_order;
     job.max_rice_param = e->cfg.max_rice_param;
-    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock;
+    // the fast kernel covers the reference's default shape: 4096-sample frames, max_rice_order 8
+    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.max_rice_order == 8;
     // the 1-D TMA bulk copy needs 16-byte aligned sources; frame strides are multiples of 16 already
     job.use_tma = ((uintptr_t)d_pcm & 15u) == 0 ? 1u : 0u;
+    const bool split_tail = tail && full;  // overlap the one-CTA last-frame launch with the full-frame kernel
+    if (split_tail) {
+        ZF_CUDA(cudaMemsetAsync(sl.d_tail_meta, 0, sizeof(unsigned long long) * 4, s));
+        ZF_CUDA(cudaEventRecord(sl.ev_in, s));
+        ZF_CUDA(cudaStreamWaitEvent(sl.aux, sl.ev_in, 0));
+        zf::FrameJob tj = job;
+        tj.pcm = d_pcm + full * e->frame_pcm_bytes;
+        tj.out = sl.d_tail;
+        tj.out_cap = e->max_frame_bytes + 64;
+        tj.frame_sizes = reinterpret_cast<uint32_t *>(sl.d_tail_meta + 2);
+        tj.desc = sl.d_tail_meta;
+        tj.total_bytes = sl.d_tail_meta + 1;
+        tj.n_frames = 1;
+        tj.frame_base = 0;
+        tj.batch_frames = 1;
+        tj.first_frame_number = first_frame_number + full;
+        tj.block_size = tail;
+        tj.ticket = sl.d_ctl + 1;
+        launch_one(e, false, 1, sl.aux, tj);
+        ZF_CUDA(cudaEventRecord(sl.ev_tail, sl.aux));
+        (*launches)++;
+    }
     if (full) {
         job.pcm = d_pcm;
         job.n_frames = (uint32_t)full;
         job.frame_base = 0;
         job.block_size = bs;
         job.ticket = sl.d_ctl + 0;
+        if (split_tail) job.batch_frames = (uint32_t)full;  // the full-frame kernel closes its own total
         const int occ = fast ? e->occ_full : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
         const uint32_t ring = sl.kev_count % kRing;
@@ -197,10 +227,15 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         sl.kev_count++;
         (*launches)++;
     }
-    if (tail) {  // the short last frame: same stream, so every earlier descriptor is final by the time it runs
-        job.pcm = d_pcm + full * e->frame_pcm_bytes;
+    if (split_tail) {
+        ZF_CUDA(cudaStreamWaitEvent(s, sl.ev_tail, 0));
+        zf::zf_append_tail_kernel<<<1, 256, 0, s>>>(sl.d_tail, reinterpret_cast<const uint32_t *>(sl.d_tail_meta + 2), d_out,
+                                                    out_cap, d_total, d_sizes, (uint32_t)full, sl.d_ctl + 2);
+        (*launches)++;
+    } else if (tail) {  // a stream shorter than one block: the short frame is the whole batch
+        job.pcm = d_pcm;
         job.n_frames = 1;
-        job.frame_base = (uint32_t)full;
+        job.frame_base = 0;
         job.block_size = tail;
         job.ticket = sl.d_ctl + 1;
         launch_one(e, false, 1, s, job);
@@ -226,6 +261,11 @@ int ensure_io(zf_encoder *e, Slot &sl) {
 int slot_init(zf_encoder *e, Slot &sl) {
     const size_t frames = e->cfg.max_frames_per_batch;
     ZF_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    ZF_CUDA(cudaStreamCreateWithFlags(&sl.aux, cudaStreamNonBlocking));
+    ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+    ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_tail, cudaEventDisableTiming));
+    ZF_CUDA(cudaMalloc(&sl.d_tail, e->max_frame_bytes + 64));
+    ZF_CUDA(cudaMalloc(&sl.d_tail_meta, sizeof(unsigned long long) * 4));
     ZF_CUDA(cudaEventCreate(&sl.ev_start));
     ZF_CUDA(cudaEventCreate(&sl.ev_stop));
     ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
@@ -241,6 +281,11 @@ int slot_init(zf_encoder *e, Slot &sl) {
 
 void slot_free(Slot &sl) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
+    if (sl.aux) cudaStreamSynchronize(sl.aux);
+    cudaFree(sl.d_tail); cudaFree(sl.d_tail_meta);
+    if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+    if (sl.ev_tail) cudaEventDestroy(sl.ev_tail);
+    if (sl.aux) cudaStreamDestroy(sl.aux);
     cudaFree(sl.d_pcm); cudaFree(sl.d_out); cudaFree(sl.d_sizes); cudaFree(sl.d_desc); cudaFree(sl.d_ctl); cudaFree(sl.d_total);
     cudaFreeHost(sl.h_pcm); cudaFreeHost(sl.h_out); cudaFreeHost(sl.h_sizes); cudaFreeHost(sl.h_total);
     if (sl.ev_start) cudaEventDestroy(sl.ev_start);

@@ -27,9 +27,9 @@
 
 namespace zf {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
-constexpr int kSpt = 16;                    // samples per thread
+constexpr int kSpt = 8;                     // samples per thread
 constexpr int kMaxBlock = kThreads * kSpt;  // 4096
 constexpr int kHalo = 4;
 constexpr int kX = kSpt + kHalo;
@@ -139,6 +139,14 @@ struct SmemCommon {
     unsigned long long levelcost[4][kMaxLevel + 1];
     uint32_t pbits[4][kNodes];
     uint32_t levelfive[4];
+    unsigned long long mixed[4][32];          // search round A, warp 0: levels 0..4 (heap node = lane)
+    unsigned long long wcost[4][2][kWarps];   // per-warp cost sums of the uniform-level warps
+    uint32_t wfive[4][2][kWarps];
+    uint32_t mixfive[4];
+    unsigned long long tot[4][kRedVals];      // block totals of pass 1 (sums, range ORs, sample OR)
+    long long warm[2][4];                     // warm-up samples of the two written subframes (thread 0)
+    uint32_t hdrw[4][4];                      // frame header words for ch_type 1, 8, 9, 10 (prepared early)
+    uint32_t hdr_len;
     SlotDec dec[4];
     uint32_t warp_scan[2][kWarps];
     uint32_t crc_part[kWarps];
@@ -164,7 +172,7 @@ struct SmemStereo {
 // ---------------------------------------------------------------------------------------------------
 
 ZF_DEVICE void init_tables(SmemCommon &c, int t) {
-    {
+    if (t < 256) {
         uint32_t v8 = (uint32_t)t, v16 = (uint32_t)t << 8;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -177,8 +185,10 @@ ZF_DEVICE void init_tables(SmemCommon &c, int t) {
     __syncthreads();
     // tab[k][b] = b * x^(8k+16) mod P : advance tab[k-1][b] by one zero byte
     for (int k = 1; k < 4; k++) {
-        const uint32_t prev = c.crc16tab[k - 1][t];
-        c.crc16tab[k][t] = (uint16_t)(((prev << 8) & 0xffffu) ^ c.crc16tab[0][prev >> 8]);
+        if (t < 256) {
+            const uint32_t prev = c.crc16tab[k - 1][t];
+            c.crc16tab[k][t] = (uint16_t)(((prev << 8) & 0xffffu) ^ c.crc16tab[0][prev >> 8]);
+        }
         __syncthreads();
     }
 }
@@ -317,10 +327,9 @@ ZF_DEVICE uint32_t header_len(unsigned long long frame_number, uint32_t n, uint3
     return 4 + number_bytes(frame_number) + be + re + 1;
 }
 
-// writes the header bytes into the (zeroed) bit buffer starting at bit 0; returns its length in bytes
-ZF_DEVICE uint32_t write_header(SmemCommon &c, uint32_t *bits, unsigned long long frame_number, uint32_t depth,
-                                uint32_t ch_type, uint32_t n, uint32_t sample_rate) {
-    uint8_t hb[16];
+// header bytes without the CRC-8; returns their count (frame_writer.zig:151-262)
+ZF_DEVICE uint32_t build_header(uint8_t (&hb)[16], unsigned long long frame_number, uint32_t depth, uint32_t ch_type,
+                                uint32_t n, uint32_t sample_rate) {
     uint32_t len = 0, be, re;
     const uint32_t bsc = block_size_code(n, be), rc = rate_code(sample_rate, re);
     hb[len++] = 0xFF;
@@ -355,14 +364,45 @@ ZF_DEVICE uint32_t write_header(SmemCommon &c, uint32_t *bits, unsigned long lon
         hb[len++] = (uint8_t)(v >> 8);
         hb[len++] = (uint8_t)v;
     }
+    return len;
+}
+
+// writes header + CRC-8 (:128-141) into the zeroed bit buffer starting at bit 0; returns its length in bytes
+ZF_DEVICE uint32_t write_header(SmemCommon &c, uint32_t *bits, unsigned long long frame_number, uint32_t depth,
+                                uint32_t ch_type, uint32_t n, uint32_t sample_rate) {
+    uint8_t hb[16];
+    uint32_t len = build_header(hb, frame_number, depth, ch_type, n, sample_rate);
     uint32_t crc = 0;
     for (uint32_t k = 0; k < len; k++) crc = c.crc8tab[crc ^ hb[k]];
     hb[len++] = (uint8_t)crc;
     for (uint32_t k = 0; k < len; k++) {
         const uint32_t sh = 24u - 8u * (k & 3u);
-        bits[k >> 2] |= (uint32_t)hb[k] << sh;  // single writer before the barrier that precedes packing
+        atomicOr(&bits[k >> 2], (uint32_t)hb[k] << sh);  // may share its last word with the first subframe
     }
     return len;
+}
+
+// Stereo frames: the header is prepared early (one thread, while others decide) for all four channel
+// assignments; CRC-8 is linear, so each variant is the base CRC xor the contribution of its ch nibble.
+ZF_DEVICE void prepare_stereo_headers(SmemCommon &c, unsigned long long frame_number, uint32_t depth, uint32_t n,
+                                      uint32_t sample_rate) {
+    uint8_t hb[16];
+    const uint32_t len = build_header(hb, frame_number, depth, 0, n, sample_rate);
+    uint32_t crc0 = 0;
+    for (uint32_t k = 0; k < len; k++) crc0 = c.crc8tab[crc0 ^ hb[k]];
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (uint32_t k = 0; k < len; k++) w[k >> 2] |= (uint32_t)hb[k] << (24u - 8u * (k & 3u));
+    const uint32_t types[4] = {1u, 8u, 9u, 10u};
+    for (uint32_t v = 0; v < 4; v++) {
+        uint32_t st = c.crc8tab[types[v] << 4];
+        for (uint32_t k = 4; k < len; k++) st = c.crc8tab[st];  // the nibble sits in byte 3; len - 4 zero bytes follow
+        const uint32_t crc = crc0 ^ st;
+        uint32_t ww[4] = {w[0], w[1], w[2], w[3]};
+        ww[0] |= types[v] << 4;  // byte 3 is the low byte of word 0
+        ww[len >> 2] |= crc << (24u - 8u * (len & 3u));
+        for (int k = 0; k < 4; k++) c.hdrw[v][k] = ww[k];
+    }
+    c.hdr_len = len + 1;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -385,11 +425,11 @@ ZF_DEVICE void unpack_stereo(const uint32_t *raw /* points at the pad */, int t,
             }
         }
     } else if (BYTES == 3) {
-        // 6 bytes per inter-channel sample; 20 samples = 120 bytes = 30 words starting at word 24t - 6
+        // 6 bytes per inter-channel sample; kX samples = kX * 6 / 4 words, 8-byte aligned start
         const uint32_t *p = raw + kRawPadWords + (kSpt * t - kHalo) * 6 / 4;
-        uint32_t w[30];
+        uint32_t w[kX * 6 / 4];
 #pragma unroll
-        for (int k = 0; k < 30; k += 2) {
+        for (int k = 0; k < kX * 6 / 4; k += 2) {
             const uint2 v = *reinterpret_cast<const uint2 *>(p + k);
             w[k] = v.x;
             w[k + 1] = v.y;
@@ -505,17 +545,27 @@ ZF_DEVICE T fixed_residual(const T (&x)[kX], uint32_t order, int j) {
 // decisions after pass 1 (one thread per slot): encoder.zig:482-527, fixed.zig:160-166, rice.zig:97-104
 // ---------------------------------------------------------------------------------------------------
 
+// cross-warp step of the pass-1 reduction: thread (slot, k) folds the kWarps partials
+ZF_DEVICE void fold_red(SmemCommon &c, int t, uint32_t nslots) {
+    if ((uint32_t)t < nslots * kRedVals) {
+        const uint32_t s = (uint32_t)t / kRedVals, k = (uint32_t)t % kRedVals;
+        unsigned long long v = 0;
+        if (k < 5) {
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) v += c.red[w][s][k];
+        } else {
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) v |= c.red[w][s][k];
+        }
+        c.tot[s][k] = v;
+    }
+}
+
 template <bool WIDE>
 ZF_DEVICE void decide_slot(SmemCommon &c, uint32_t slot, uint32_t depth_ch, uint32_t n, const FrameJob &job) {
-    unsigned long long tot[5], rng[5], orv = 0;
-    for (int k = 0; k < 5; k++) { tot[k] = 0; rng[k] = 0; }
-    for (int w = 0; w < kWarps; w++) {
-        for (int k = 0; k < 5; k++) {
-            tot[k] += c.red[w][slot][k];
-            rng[k] |= c.red[w][slot][5 + k];
-        }
-        orv |= c.red[w][slot][10];
-    }
+    unsigned long long tot[5], rng[5];
+    for (int k = 0; k < 5; k++) { tot[k] = c.tot[slot][k]; rng[k] = c.tot[slot][5 + k]; }
+    unsigned long long orv = c.tot[slot][10];
     SlotDec d;
     d.depth = depth_ch;
     // calcWasteBits, encoder.zig:556-570: OR over the samples as integers of the plane's width
@@ -602,8 +652,8 @@ ZF_DEVICE void best_param(unsigned long long S, uint32_t B, uint32_t n, uint32_t
 // ---------------------------------------------------------------------------------------------------
 
 template <bool WIDE, bool FULL, int MODE>
-ZF_DEVICE uint32_t emit_subframe(const typename Ar<WIDE>::T (&x)[kX], int t, uint32_t base, uint32_t n, const SlotDec &d,
-                                 const uint8_t *choice_row, uint32_t *bits, uint32_t pos) {
+ZF_DEVICE uint32_t emit_plain(const typename Ar<WIDE>::T (&x)[kX], int t, uint32_t base, uint32_t n, const SlotDec &d,
+                              uint32_t *bits, uint32_t pos) {
     typedef typename Ar<WIDE>::T T;
     BitWriter bw;
     const uint32_t start = pos;
@@ -650,6 +700,18 @@ ZF_DEVICE uint32_t emit_subframe(const typename Ar<WIDE>::T (&x)[kX], int t, uin
         bw.finish();
         return p - start;
     }
+    return 0;
+}
+
+template <bool WIDE, bool FULL, int MODE>
+ZF_DEVICE uint32_t emit_subframe(const typename Ar<WIDE>::T (&x)[kX], int t, uint32_t base, uint32_t n, const SlotDec &d,
+                                 const uint8_t *choice_row, uint32_t *bits, uint32_t pos) {
+    typedef typename Ar<WIDE>::T T;
+    if (d.kind != kFixed) return emit_plain<WIDE, FULL, MODE>(x, t, base, n, d, bits, pos);
+    BitWriter bw;
+    const uint32_t start = pos;
+    if (MODE == 1) bw.init(bits, pos);
+    const uint32_t unary = d.waste;
     // FIXED :303-361
     const uint32_t order = d.order, waste = d.waste;
     const uint32_t psz = n >> d.po;
@@ -909,22 +971,6 @@ ZF_DEVICE void finish_frame(SmemCommon &c, uint32_t *bits, int t, const FrameJob
     const int lane = t & 31, warp = t >> 5;
     const uint32_t fbytes = (total_bits + 7u) >> 3;  // zero padded to a byte (frame_writer.zig:114-117)
     const uint32_t size = fbytes + 2u;
-    // --- CRC-16 over fbytes: 128-byte chunks, each multiplied by x^(8 * bytes-after-it) mod P ---
-    uint32_t contrib = 0;
-    const uint32_t nchunks = fits ? ((fbytes + 127u) >> 7) : 0u;
-    for (uint32_t ck = t; ck < nchunks; ck += kThreads) {
-        const uint32_t cb = (fbytes - (ck << 7)) < 128u ? (fbytes - (ck << 7)) : 128u;
-        const uint32_t words = cb >> 2, tail = cb & 3u;
-        const uint32_t *p = bits + (ck << 5);
-        uint32_t crc = 0;
-        for (uint32_t w = 0; w < words; w++) crc = crc16_word(c, crc, p[w]);
-        for (uint32_t k = 0; k < tail; k++) crc = crc16_byte(c, crc, (p[words] >> (24u - 8u * k)) & 0xffu);
-        const uint32_t dist = fbytes - ((ck << 7) + cb);
-        contrib ^= crc16_mulmod(c, crc, job.pow8[dist]);
-    }
-    contrib = reduce_xor(contrib);
-    if (lane == 0) c.crc_part[warp] = contrib;
-    __syncthreads();
     if (warp == 0) {
         // --- look-back over the frame-size descriptors of the batch (single-pass stream compaction) ---
         unsigned long long excl = 0;
@@ -946,20 +992,47 @@ ZF_DEVICE void finish_frame(SmemCommon &c, uint32_t *bits, int t, const FrameJob
             }
         }
         if (lane == 0) {
-            uint32_t crc = 0;
-            for (int w = 0; w < kWarps; w++) crc ^= c.crc_part[w];
-            // append CRC-16 big-endian at byte fbytes (frame_writer.zig:144-148)
-            if (fits) {
-                const uint32_t bp = fbytes << 3;
-                const uint32_t wi = bp >> 5, off = bp & 31u;
-                if (off <= 16u) bits[wi] |= crc << (16u - off);
-                else { bits[wi] |= crc >> (off - 16u); bits[wi + 1] |= crc << (48u - off); }
-            }
             c.out_off = excl;
             st_relaxed_gpu(job.desc + fidx, kFlagPrefix | (excl + size));
             if (fidx + 1 == job.batch_frames) *job.total_bytes = excl + size;
             if (excl + size > job.out_cap) atomicOr(job.status, kStatusOutOverflow);
         }
+    } else {
+        // --- CRC-16 over fbytes (warps 1..): 64-byte chunks, each multiplied by x^(8 * bytes-after-it) mod P ---
+        uint32_t contrib = 0;
+        const uint32_t nchunks = fits ? ((fbytes + 63u) >> 6) : 0u;
+        for (uint32_t ck = (uint32_t)t - 32u; ck < nchunks; ck += kThreads - 32) {
+            const uint32_t cb = (fbytes - (ck << 6)) < 64u ? (fbytes - (ck << 6)) : 64u;
+            const uint32_t *p = bits + (ck << 4);
+            uint32_t crc = 0;
+            if (cb == 64u) {
+#pragma unroll
+                for (uint32_t w = 0; w < 16; w += 4) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(p + w);
+                    crc = crc16_word(c, crc, v.x);
+                    crc = crc16_word(c, crc, v.y);
+                    crc = crc16_word(c, crc, v.z);
+                    crc = crc16_word(c, crc, v.w);
+                }
+            } else {
+                const uint32_t words = cb >> 2, tail = cb & 3u;
+                for (uint32_t w = 0; w < words; w++) crc = crc16_word(c, crc, p[w]);
+                for (uint32_t k = 0; k < tail; k++) crc = crc16_byte(c, crc, (p[words] >> (24u - 8u * k)) & 0xffu);
+            }
+            const uint32_t dist = fbytes - ((ck << 6) + cb);
+            contrib ^= crc16_mulmod(c, crc, job.pow8[dist]);
+        }
+        contrib = reduce_xor(contrib);
+        if (lane == 0) c.crc_part[warp] = contrib;
+    }
+    __syncthreads();
+    if (t == 0 && fits) {  // append CRC-16 big-endian at byte fbytes (frame_writer.zig:144-148)
+        uint32_t crc = 0;
+        for (int w = 1; w < kWarps; w++) crc ^= c.crc_part[w];
+        const uint32_t bp = fbytes << 3;
+        const uint32_t wi = bp >> 5, off = bp & 31u;
+        if (off <= 16u) bits[wi] |= crc << (16u - off);
+        else { bits[wi] |= crc >> (off - 16u); bits[wi + 1] |= crc << (48u - off); }
     }
     __syncthreads();
     // --- byte-shifted copy shared -> global: head bytes, aligned 32-bit words, tail bytes ---
@@ -1088,6 +1161,8 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_kernel(const Fra
             if (lane == 0) c.red[warp][s][10] = wo;
         }
         __syncthreads();
+        fold_red(c, t, 4);
+        __syncthreads();
         if (t < 4) decide_slot<WIDE>(c, (uint32_t)t, depth + (t == 3 ? 1u : 0u), n, job);
         __syncthreads();
 
@@ -1165,6 +1240,27 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_kernel(const Fra
         __syncthreads();
         if (t == 0) c.cur_frame = c.next_frame;
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The short last frame of a stream is encoded by a one-CTA launch that runs concurrently with the
+// full-frame kernel (its own stream, private output); this kernel appends it to the compacted stream.
+// ---------------------------------------------------------------------------------------------------
+__global__ void zf_append_tail_kernel(const uint8_t *tail, const uint32_t *tail_size, uint8_t *out,
+                                      unsigned long long out_cap, unsigned long long *total, uint32_t *frame_sizes,
+                                      uint32_t fidx, unsigned int *status) {
+    const uint32_t size = *tail_size;
+    const unsigned long long off = *total;
+    if (off + size > out_cap) {
+        if (threadIdx.x == 0) atomicOr(status, kStatusOutOverflow);
+        return;
+    }
+    for (uint32_t k = threadIdx.x; k < size; k += blockDim.x) out[off + k] = tail[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        frame_sizes[fidx] = size;
+        *total = off + size;
     }
 }
 

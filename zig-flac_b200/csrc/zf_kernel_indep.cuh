@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_indep_kernel(const Fram
             const unsigned long long wo = warp_or(p.orv);
             if (lane == 0) c.red[warp][0][10] = wo;
             __syncthreads();
+            fold_red(c, t, 1);
+            __syncthreads();
             if (t == 0) decide_slot<WIDE>(c, 0, depth, n, job);
             __syncthreads();
             rice_zero_leaves(c, 0, t, n);
