@@ -325,10 +325,10 @@ def main():
             "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
-                         "kernel": "zf_encode_stereo_kernel<3,true>" if bits == 24 else "zf_encode_stereo_kernel",
+                         "kernel": ("zf::v3::zf_encode_stereo_v3_kernel<%d>" % (bits // 8)) if bits != 32 and not os.environ.get("ZF_LEGACY_KERNEL") else ("zf::zf_encode_stereo_full_kernel<%d>" % (bits // 8)),
                          "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": kernel_bytes,
                          "peak_source": peak_src,
-                         "note": "integer-issue bound, not HBM bound: see DESIGN.md (about 150 integer ops per inter-channel sample)"},
+                         "note": "integer-issue bound, not HBM bound: see DESIGN.md section 4"},
             "parity": {"device_path_equals_host_path": same},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -45,6 +45,15 @@ static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) {
     sh &= 31u;
     return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
 }
+static inline uint32_t __funnelshift_lc(uint32_t lo, uint32_t hi, uint32_t sh) {  // shift clamped to 32
+    if (sh >= 32u) return lo;
+    return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+    sh &= 31u;
+    return sh ? ((lo >> sh) | (hi << (32u - sh))) : lo;
+}
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 
 template <typename T>
 static inline T emu_exchange(T v, int src_lane_rel_mode, int arg) {
@@ -79,7 +88,8 @@ static inline uint32_t emu_warp_fold(uint32_t v, int op) {
         if (op == 0) r += x;
         else if (op == 1) r |= x;
         else if (op == 2) r ^= x;
-        else r = x > r ? x : r;
+        else if (op == 3) r = x > r ? x : r;
+        else r = (l == 0 || x < r) ? x : r;
     }
     emu::warp_barrier();
     return r;
@@ -118,4 +128,5 @@ static inline uint32_t reduce_add(uint32_t v) { return emu_warp_fold(v, 0); }
 static inline uint32_t reduce_or(uint32_t v) { return emu_warp_fold(v, 1); }
 static inline uint32_t reduce_xor(uint32_t v) { return emu_warp_fold(v, 2); }
 static inline uint32_t reduce_max(uint32_t v) { return emu_warp_fold(v, 3); }
+static inline uint32_t reduce_min(uint32_t v) { return emu_warp_fold(v, 4); }
 }  // namespace zf

@@ -9,11 +9,12 @@
 #define ZF_HOST_EMU 1
 #include "cuda_emu.h"
 
-namespace zf { alignas(128) unsigned char zf_smem[256 * 1024]; }
+namespace zf { alignas(128) unsigned char zf_smem[256 * 1024]; namespace v3 { alignas(128) unsigned char zf_smem[256 * 1024]; } }
 
 #include "../../zig-flac_b200/csrc/zf_kernel.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_indep.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_full.cuh"
+#include "../../zig-flac_b200/csrc/zf_kernel_v3.cuh"
 
 namespace emu {
 emu_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
@@ -108,13 +109,20 @@ void run_block(void (*fn)(void *), void *arg, int nthreads) {
 }  // namespace emu
 
 static zf::FrameJob g_job;
-static int g_bytes, g_full, g_indep;
+static int g_bytes, g_full, g_indep, g_v3;
+static int g_allow_v3 = 1;
+static unsigned long long g_v3_frames = 0;
 
 static void kernel_entry(void *) {
     if (g_indep) {
         if (g_bytes == 2) zf::zf_encode_indep_kernel<2>(g_job);
         else if (g_bytes == 3) zf::zf_encode_indep_kernel<3>(g_job);
         else zf::zf_encode_indep_kernel<4>(g_job);
+        return;
+    }
+    if (g_v3) {
+        if (g_bytes == 2) zf::v3::zf_encode_stereo_v3_kernel<2>(g_job);
+        else zf::v3::zf_encode_stereo_v3_kernel<3>(g_job);
         return;
     }
     if (g_full) {
@@ -168,9 +176,14 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     if (full) {
         j.pcm = pcm; j.n_frames = (uint32_t)full; j.frame_base = 0; j.block_size = block_size;
         g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8;
+        g_v3 = g_full && g_allow_v3 && bytes_per_sample != 4 && max_rice_param == 30;
         g_job = j;
         ticket = 0;
-        emu::run_block(kernel_entry, nullptr, zf::kThreads);
+        if (g_v3) g_v3_frames += full;
+        emu::g_blockDim.x = g_v3 ? zf::v3::kT : zf::kThreads;
+        emu::run_block(kernel_entry, nullptr, g_v3 ? zf::v3::kT : zf::kThreads);
+        emu::g_blockDim.x = zf::kThreads;
+        g_v3 = 0;
     }
     if (tail) {
         j.pcm = pcm + full * j.frame_stride; j.n_frames = 1; j.frame_base = (uint32_t)full; j.block_size = tail;
@@ -182,6 +195,16 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     if (n_frames_out) *n_frames_out = (uint32_t)frames;
     if (status) return -(long long)status;
     return (long long)total;
+}
+
+void emu_allow_v3(int on) { g_allow_v3 = on; }
+unsigned long long emu_v3_frames(void) { return g_v3_frames; }
+
+void emu_best_param_nw(unsigned long long S, unsigned B, unsigned n, unsigned P, unsigned *choice, unsigned long long *cost) {
+    uint32_t c, k;
+    zf::v3::best_param_nw(S, B, n, P, c, k);
+    *choice = c;
+    *cost = k;
 }
 
 // exhaustive-ish check hook for the closed-form parameter search

@@ -23,7 +23,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "zig-flac_b200", "csrc")
 @pytest.fixture(scope="module")
 def emu():
     srcs = [os.path.join(EMU_DIR, f) for f in ("emu_main.cpp", "cuda_emu.h")] + [
-        os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_kernel_full.cuh", "zf_dev.h")]
+        os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_kernel_full.cuh", "zf_kernel_v3.cuh", "zf_dev.h")]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
         os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", EMU_SO,
@@ -114,3 +114,50 @@ def test_independent_channel_kernel_logic(emu, oracle, channels):
         planes = [rng.integers(-F // 4, F // 4, n) if c % 2 else np.cumsum(rng.integers(-9, 10, n)) for c in range(channels)]
         pcm = oracle.pcm_bytes_from_int(signals.interleave(planes), bits)
         _check(emu, oracle, pcm, n, bits, channels=channels, rate=48000)
+
+
+def test_v3_parameter_search_equals_brute_force(emu, oracle):
+    """v3::best_param_nw (32-bit costs, widths <= 31, P in {14, 30}) against the reference's loop (rice.zig:359-379)."""
+    emu.emu_best_param_nw.argtypes = [C.c_ulonglong, C.c_uint, C.c_uint, C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)]
+    rng = np.random.default_rng(3)
+    f = oracle.lib().zo_flac_calc_part_size
+    for _ in range(30000):
+        n = int(rng.choice([12, 13, 14, 15, 16, 32, 64, 128, 256, 512, 1024, 2048, 4092, 4096]))
+        S = int(rng.integers(0, 1 << int(rng.integers(1, 41))))
+        if rng.random() < 0.3:
+            S = int(rng.integers(0, 6 * n + 3))
+        B, P = int(rng.integers(0, 27)), int(rng.choice([14, 30]))
+        best, ch = 5 + B * n, 0x80 | B
+        for p in range(P):
+            c = f(n, p, S)
+            if c < best:
+                best, ch = c, p
+        c_out, k_out = C.c_uint(), C.c_ulonglong()
+        emu.emu_best_param_nw(S, B, n, P, C.byref(c_out), C.byref(k_out))
+        assert (c_out.value, k_out.value) == (ch, best), (S, B, n, P)
+
+
+@pytest.mark.parametrize("bits", [16, 24])
+def test_v3_kernel_multi_frame_streams(emu, oracle, bits):
+    """The lean 256-thread kernel (zf_kernel_v3.cuh) on multi-frame streams: persistent loop, look-back offsets of
+    odd-sized frames, every stereo mode, escape partitions, wasted bits, frame numbers with long UTF-8 codes."""
+    import zigflac_b200 as zf
+    n = 5 * 4096
+    pcm = zf.synth_pcm(n, 44100 if bits == 16 else 96000, bits)
+    _check(emu, oracle, pcm, n, bits, rate=44100 if bits == 16 else 96000)
+    _check(emu, oracle, pcm, n, bits, rate=96000, first=(1 << 21) - 2)
+    rng = np.random.default_rng(bits)
+    F = 1 << (bits - 1)
+    t = np.arange(n)
+    env = (0.02 + 0.98 * np.sin(2 * np.pi * t / 3000.0) ** 8)
+    L = (0.45 * F * env * np.sin(2 * np.pi * 997 * t / 48000)).astype(np.int64) + rng.integers(-2, 3, n)
+    R = (L * 0.9).astype(np.int64) + np.where(rng.random(n) < 0.003, rng.integers(-F // 2, F // 2, n), 0)
+    R = np.clip(R, -F, F - 1)
+    R[4096:4096 + 2048] &= ~0xff
+    L[4096:4096 + 2048] &= ~0xf
+    pcm = oracle.pcm_bytes_from_int(signals.interleave([L, R]), bits)
+    _check(emu, oracle, pcm, n, bits, rate=48000)
+    for name, a, b in signals.stereo_classes(bits, n=2 * 4096):
+        _check(emu, oracle, oracle.pcm_bytes_from_int(signals.interleave([a, b]), bits), a.size, bits)
+    emu.emu_v3_frames.restype = C.c_ulonglong
+    assert emu.emu_v3_frames() >= 15 + 2 * 18  # the streams above really went through the v3 kernel

@@ -28,7 +28,7 @@ def build(force=False, verbose=False):
     cu = [os.path.join(CSRC, f) for f in ("zf_capi.cu",)]
     cpp = [os.path.join(CSRC, f) for f in ("zf_host.cpp", "zf_driver.cpp")]
     c = [os.path.join(CSRC, "zf_synth.c")]
-    hdr = [os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_kernel_full.cuh", "zf_dev.h")] + [
+    hdr = [os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_kernel_full.cuh", "zf_kernel_v3.cuh", "zf_dev.h")] + [
         os.path.join(HERE, "..", "include", "zigflac_b200.h")]
     if force or _stale(LIB, cu + cpp + c + hdr + [os.path.abspath(__file__)]):
         synth_o = os.path.join(CSRC, "zf_synth.o")

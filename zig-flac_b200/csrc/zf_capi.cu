@@ -17,6 +17,7 @@
 #include "zf_kernel.cuh"
 #include "zf_kernel_indep.cuh"
 #include "zf_kernel_full.cuh"
+#include "zf_kernel_v3.cuh"
 
 namespace {
 
@@ -73,8 +74,10 @@ struct zf_encoder {
     size_t frame_pcm_bytes = 0;
     size_t max_frame_bytes = 0;
     bool stereo = false;
-    int occ_full = 0, occ_gen = 0;
+    bool force_legacy = false;  // ZF_LEGACY_KERNEL=1: A/B against the 512-thread kernel (development aid)
+    int occ_full = 0, occ_gen = 0, occ_v3 = 0;
     size_t smem_stereo = 0;
+    size_t smem_v3 = 0;
     size_t smem_indep = 0;
 };
 
@@ -103,6 +106,16 @@ int setup_stereo_kernel(zf_encoder *e, int *occ) {
 }
 
 template <int BYTES>
+int setup_v3_kernel(zf_encoder *e, int *occ) {
+    auto k = zf::v3::zf_encode_stereo_v3_kernel<BYTES>;
+    const size_t smem = sizeof(zf::v3::Smem<BYTES>);
+    ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, zf::v3::kT, smem));
+    e->smem_v3 = smem;
+    return ZF_OK;
+}
+
+template <int BYTES>
 int setup_indep_kernel(zf_encoder *e, int *occ) {
     auto k = zf::zf_encode_indep_kernel<BYTES>;
     const size_t smem = zf::indep_smem_bytes(BYTES, e->cfg.channels);
@@ -116,8 +129,8 @@ int setup_kernels(zf_encoder *e) {
     const int bytes = e->cfg.bit_depth / 8;
     int rc = ZF_OK;
     if (e->stereo) {
-        if (bytes == 2) { rc = setup_stereo_kernel<2, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<2, false>(e, &e->occ_gen); }
-        else if (bytes == 3) { rc = setup_stereo_kernel<3, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<3, false>(e, &e->occ_gen); }
+        if (bytes == 2) { rc = setup_stereo_kernel<2, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<2, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<2>(e, &e->occ_v3); }
+        else if (bytes == 3) { rc = setup_stereo_kernel<3, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<3, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<3>(e, &e->occ_v3); }
         else { rc = setup_stereo_kernel<4, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<4, false>(e, &e->occ_gen); }
     } else {
         if (bytes == 2) rc = setup_indep_kernel<2>(e, &e->occ_gen);
@@ -218,11 +231,18 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         job.block_size = bs;
         job.ticket = sl.d_ctl + 0;
         if (split_tail) job.batch_frames = (uint32_t)full;  // the full-frame kernel closes its own total
-        const int occ = fast ? e->occ_full : e->occ_gen;
+        // 16/24-bit with the default Rice limits: the lean 256-thread kernel (zf_kernel_v3.cuh)
+        const bool v3 = fast && e->cfg.bit_depth != 32 && e->cfg.max_rice_param == 30 && e->occ_v3 > 0 && !e->force_legacy;
+        const int occ = v3 ? e->occ_v3 : fast ? e->occ_full : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
         const uint32_t ring = sl.kev_count % kRing;
         ZF_CUDA(cudaEventRecord(sl.kev[2 * ring], s));
-        launch_one(e, fast, grid, s, job);
+        if (v3) {
+            if (e->cfg.bit_depth == 16) zf::v3::zf_encode_stereo_v3_kernel<2><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
+            else zf::v3::zf_encode_stereo_v3_kernel<3><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
+        } else {
+            launch_one(e, fast, grid, s, job);
+        }
         ZF_CUDA(cudaEventRecord(sl.kev[2 * ring + 1], s));
         sl.kev_count++;
         (*launches)++;
@@ -434,6 +454,7 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     if (!e) return ZF_ERR_NOMEM;
     e->cfg = *cfg;
     e->stereo = cfg->channels == 2 && cfg->stereo_decorrelation;
+    { const char *lg = getenv("ZF_LEGACY_KERNEL"); e->force_legacy = lg && lg[0] == '1'; }
     e->frame_pcm_bytes = (size_t)cfg->block_size * cfg->channels * (cfg->bit_depth / 8);
     e->max_frame_bytes = max_frame_bytes_of(cfg);
     cudaDeviceProp prop;

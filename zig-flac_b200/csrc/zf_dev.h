@@ -68,6 +68,7 @@ ZF_DEVICE uint32_t reduce_add(uint32_t v) { return __reduce_add_sync(0xffffffffu
 ZF_DEVICE uint32_t reduce_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
 ZF_DEVICE uint32_t reduce_xor(uint32_t v) { return __reduce_xor_sync(0xffffffffu, v); }
 ZF_DEVICE uint32_t reduce_max(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+ZF_DEVICE uint32_t reduce_min(uint32_t v) { return __reduce_min_sync(0xffffffffu, v); }
 
 }  // namespace zf
 #endif
