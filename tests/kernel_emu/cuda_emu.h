@@ -19,6 +19,7 @@
 
 struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };
+struct ulonglong2 { unsigned long long x, y; };
 struct emu_dim3 { unsigned x, y, z; };
 
 namespace emu {
@@ -99,6 +100,8 @@ static inline uint32_t __ballot_sync(unsigned, int pred) {
     return emu_warp_fold(pred ? (1u << lane) : 0u, 1);
 }
 
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
+
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 static inline uint32_t atomicOr(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
@@ -122,6 +125,9 @@ static inline void fence_proxy_async() {}
 static inline void mbar_expect_tx(unsigned long long *, uint32_t) {}
 static inline void mbar_wait(unsigned long long *, uint32_t) {}
 static inline void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *) { memcpy(dst, src, bytes); }
+static inline void cp_async16_cg(void *dst, const void *src) { memcpy(dst, src, 16); }
+static inline void cp_async_commit() {}
+static inline void cp_async_wait_all() {}
 static inline void st_relaxed_gpu(unsigned long long *p, unsigned long long v) { *p = v; }
 static inline unsigned long long ld_relaxed_gpu(const unsigned long long *p) { return *p; }
 static inline uint32_t reduce_add(uint32_t v) { return emu_warp_fold(v, 0); }

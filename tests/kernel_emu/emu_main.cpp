@@ -176,7 +176,9 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     if (full) {
         j.pcm = pcm; j.n_frames = (uint32_t)full; j.frame_base = 0; j.block_size = block_size;
         g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8;
-        g_v3 = g_full && g_allow_v3 && bytes_per_sample != 4 && max_rice_param == 30;
+        bool table = false;
+        for (unsigned r : {88200u, 176400u, 192000u, 8000u, 16000u, 22050u, 24000u, 32000u, 44100u, 48000u, 96000u}) table |= r == sample_rate;
+        g_v3 = g_full && g_allow_v3 && bytes_per_sample != 4 && max_rice_param == 30 && table;
         g_job = j;
         ticket = 0;
         if (g_v3) g_v3_frames += full;

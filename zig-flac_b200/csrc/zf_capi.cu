@@ -85,6 +85,15 @@ namespace {
 
 bool depth_ok(unsigned d) { return d == 16 || d == 24 || d == 32; }
 
+// sample rates with a frame-header code of their own (frame_writer.zig:187-217); others take the general kernels
+bool table_rate(uint32_t r) {
+    switch (r) {
+        case 88200: case 176400: case 192000: case 8000: case 16000: case 22050: case 24000: case 32000: case 44100:
+        case 48000: case 96000: return true;
+        default: return false;
+    }
+}
+
 size_t max_frame_bytes_of(const zf_config *cfg) {
     // encoder.zig:583-595 with the reference's own call-site quirk (:59 passes compute_waste_bits = true)
     const size_t header_max = 2 + 7 + 2 + 2 + 1, subframe_header_max = 8, footer = 2;
@@ -232,7 +241,8 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         job.ticket = sl.d_ctl + 0;
         if (split_tail) job.batch_frames = (uint32_t)full;  // the full-frame kernel closes its own total
         // 16/24-bit with the default Rice limits: the lean 256-thread kernel (zf_kernel_v3.cuh)
-        const bool v3 = fast && e->cfg.bit_depth != 32 && e->cfg.max_rice_param == 30 && e->occ_v3 > 0 && !e->force_legacy;
+        const bool v3 = fast && e->cfg.bit_depth != 32 && e->cfg.max_rice_param == 30 && e->occ_v3 > 0 && !e->force_legacy &&
+                        table_rate(e->cfg.sample_rate);
         const int occ = v3 ? e->occ_v3 : fast ? e->occ_full : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
         const uint32_t ring = sl.kev_count % kRing;

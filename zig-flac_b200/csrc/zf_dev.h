@@ -54,6 +54,13 @@ ZF_DEVICE void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
                  : "memory");
 }
 
+// ---- Ampere-style asynchronous copy, L2 only (.cg): used to fetch look-back descriptors without holding registers
+ZF_DEVICE void cp_async16_cg(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+ZF_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+ZF_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- look-back descriptors: one 64-bit word carries flag + value, so relaxed gpu-scope accesses suffice
 ZF_DEVICE void st_relaxed_gpu(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

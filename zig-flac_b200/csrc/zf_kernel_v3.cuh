@@ -1,22 +1,35 @@
 // zf_kernel_v3.cuh -- lean full-frame stereo kernel for 16- and 24-bit PCM (block 4096, max_rice_order 8,
-// max_rice_param 30).  Same decisions and the same bytes as zf_kernel.cuh / the oracle, arranged around the
-// B200's issue limits (the path is integer-issue bound, not HBM bound -- DESIGN.md section 4):
+// max_rice_param 30, a sample rate with a header code of its own).  Same decisions and the same bytes as
+// zf_kernel.cuh / the oracle, arranged around the B200's issue limits (the path is integer-issue bound, not HBM
+// bound -- DESIGN.md section 4):
 //
 //   * 256 threads x 16 samples: a thread owns exactly one finest Rice partition (level 8), so leaf statistics
-//     never leave registers; 3 CTAs per SM overlap each other's barriers
-//   * samples are NOT kept in registers across phases: every phase re-unpacks its 20-sample window from the raw
-//     PCM in shared memory (8 LDS.128 + PRMT), which keeps the kernel spill-free at 80 registers
+//     never leave registers; 3 CTAs per SM overlap each other's barriers; 80 registers, no spills
+//   * samples are NOT kept in registers across phases: every phase re-reads its window from the raw PCM in shared
+//     memory; pass 1 streams it four samples at a time through one rolled piece of code (all four candidates side
+//     by side) -- the kernel's code size matters as much as its instruction count (32 KB instruction cache)
 //   * all arithmetic is 32-bit (|delta^4| < 2^28, 16-sample sums < 2^32); only tree sums above a leaf are 64-bit
-//   * pass 1 keeps the five per-leaf abs-sums in registers, so pass 2 only needs min/max of the chosen order
-//   * one barrier per decision: decisions are taken by one warp and broadcast through shared memory
-//   * bit writer: right-aligned 64-bit shift register, one funnel shift + one shared atomicOr per 32 output bits
+//   * decisions that every thread needs (partition order, method, FIXED vs VERBATIM, stereo mode) are computed
+//     redundantly by every warp from shared per-level partial sums: no decision barrier, no broadcast
+//   * bit writer: right-aligned 64-bit shift register; a word is stored (plain, predicated) by the one thread whose
+//     bit range crosses the word's end, partial tail words are ORed in after a barrier; the two subframes are
+//     written as two interleaved dependency chains
 //   * the stream is placed in the bit buffer so that it ENDS on a 16-byte boundary (leading zero bytes do not change
 //     a CRC with zero init), CRC-16 is computed table-free in GF(2)[x]/(x^15+x+1) x parity
 //     (x^16+x^15+x^2+1 = (x+1)(x^15+x+1)): Horner step  a <- a*(x^4+x^2) + word,  x^32 = x^4+x^2 (mod x^15+x+1)
+//   * deferred epilogue: a finished frame stays in the bit buffer while the next one is analysed; its output offset
+//     comes from a decoupled look-back whose descriptor window is fetched with cp.async (no registers, no waiting),
+//     and it is copied out (16-byte stores) just before the bit buffer is needed again
 //
 // Reference call stack mirrored per frame: Encoder.writeFrame, encoder.zig:234-284 (see zf_kernel.cuh).
 #pragma once
 #include "zf_kernel.cuh"
+
+#ifdef ZF_HOST_EMU
+#define ZF_NOINLINE inline
+#else
+#define ZF_NOINLINE __device__ __noinline__
+#endif
 
 namespace zf {
 namespace v3 {
@@ -28,33 +41,38 @@ constexpr int kXn = kS + kH;
 constexpr int kN = 4096;
 constexpr int kW = kT / 32;
 constexpr int kPadWords = 8;     // 32 zero bytes in front of the PCM: history of thread 0
-constexpr int kCrcChunkWords = 32;
-#ifndef ZF_V3_MIN_CTAS
-#define ZF_V3_MIN_CTAS 3
-#endif
+constexpr int kCrcChunkWords = 16;
+constexpr int kCtasPerSm = 3;    // 80 registers, ~66 KB of shared memory each
 
-struct Dec {  // per candidate channel
-    uint32_t kind, order, waste, bps, P, po, method, est;
+struct Dec {  // per candidate channel, after pass 1
+    uint32_t kind, order, waste, bps, P, est;
+    uint32_t pad[2];
+};
+
+// scratch of the analysis phases
+struct Scratch {
+    unsigned long long node[4][256];  // heap nodes 8..255 (levels 3..7): abs-sum | width << 48
+    uint32_t red[kW][4][12];          // pass-1 warp partials: 5 x (lo, hi) + sample OR
 };
 
 template <int BYTES>
 struct Smem {
     alignas(16) uint32_t raw[kPadWords + kN * 2 * BYTES / 4];
     alignas(16) uint32_t bits[BitBufWords<BYTES>::value + 8];
+    alignas(16) uint32_t lvlcost[4][9][16];  // per candidate, per partition order: up to 16 partial cost sums
+    alignas(16) uint8_t lvlfive[4][9][16];   // ... and whether a parameter > 14 occurs (5-bit method, rice.zig:383-387)
+    alignas(16) Scratch sc;
+    alignas(16) unsigned long long lbwin[128];  // look-back window: descriptors hi-127 .. hi (fetched by cp.async)
+    unsigned long long lb_excl;                // bytes of the predecessors examined so far
+    int32_t lb_i;                              // nearest predecessor not examined yet
+    uint32_t lb_done;
     unsigned long long mbar;
     unsigned long long out_off;
-    unsigned long long node[4][256];  // heap nodes 8..255 (levels 3..7): abs-sum | width << 48
-    uint32_t red[kW][4][12];          // pass-1 warp partials: 5 x (lo, hi) + sample OR
-    uint32_t mixed[4][32];            // round-B costs of heap nodes 1..31 (levels 0..4)
-    uint32_t wcostA[4][kW];           // level-8 cost per warp
-    uint32_t wcostB[4][kW];           // round-B cost per warp (warps 1..7 hold levels 5, 6, 6, 7, 7, 7, 7)
-    uint32_t wfiveA[4][kW], wfiveB[4][kW];
-    uint32_t mixfive[4];
     Dec dec[4];
     int32_t warm[4][4];               // first four samples of every candidate (warm-ups, CONSTANT value)
     uint32_t scan[2][kW];
     uint32_t crc_part[kW], par_part[kW];
-    uint32_t cur_frame, next_frame;
+    uint32_t next_frame;
     uint8_t crc8tab[256];
     uint8_t choice[4][512];           // heap node m (1..511) -> Rice parameter, or 0x80 | escape width
 };
@@ -72,7 +90,8 @@ ZF_DEVICE uint32_t shl32(uint32_t v, uint32_t s) {
 #endif
 }
 
-template <int BYTES>
+// WHICH: 0 both channels, 1 left only, 2 right only (the other array is left untouched)
+template <int BYTES, int WHICH>
 ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (&R)[kXn]) {
     if (BYTES == 2) {
         // one word per inter-channel sample; the window starts 4 samples before 16 t
@@ -83,8 +102,8 @@ ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                L[4 * k + q] = (int32_t)prmt(w[q], 0, 0x9910);
-                R[4 * k + q] = (int32_t)prmt(w[q], 0, 0xBB32);
+                if (WHICH != 2) L[4 * k + q] = (int32_t)prmt(w[q], 0, 0x9910);
+                if (WHICH != 1) R[4 * k + q] = (int32_t)prmt(w[q], 0, 0xBB32);
             }
         }
     } else {
@@ -100,6 +119,57 @@ ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (
 #pragma unroll
         for (int k = 0; k < kXn / 2; k++) {  // two inter-channel samples per three words
             const uint32_t a = w[2 + 3 * k], b = w[3 + 3 * k], d = w[4 + 3 * k];
+            if (WHICH != 2) {
+                L[2 * k] = (int32_t)prmt(a, b, 0xA210);
+                L[2 * k + 1] = (int32_t)prmt(b, d, 0xC432);
+            }
+            if (WHICH != 1) {
+                R[2 * k] = (int32_t)prmt(a, b, 0xD543);
+                R[2 * k + 1] = (int32_t)prmt(d, 0, 0xB321);
+            }
+        }
+    }
+}
+
+// candidate channel `slot` (uniform over the block) of a stereo frame: 0 L, 1 R, 2 M = (L + R) >> 1, 3 S = L - R
+// (encoder.zig:330-350).  Every arm produces x directly, so no register copies are needed to merge them.
+template <int BYTES>
+ZF_DEVICE void load_x(const uint32_t *raw, int t, uint32_t slot, int32_t (&x)[kXn]) {
+    if (slot == 0) {
+        unpack20<BYTES, 1>(raw, t, x, x);
+    } else if (slot == 1) {
+        unpack20<BYTES, 2>(raw, t, x, x);
+    } else {
+        int32_t R[kXn];
+        unpack20<BYTES, 0>(raw, t, x, R);
+        if (slot == 2) {
+#pragma unroll
+            for (int i = 0; i < kXn; i++) x[i] = (x[i] + R[i]) >> 1;
+        } else {
+#pragma unroll
+            for (int i = 0; i < kXn; i++) x[i] = x[i] - R[i];
+        }
+    }
+}
+
+// four consecutive inter-channel samples starting at sample index i0 (may be -4: the zero pad) of the frame in `raw`
+template <int BYTES>
+ZF_DEVICE void load4(const uint32_t *raw, int i0, int32_t (&L)[4], int32_t (&R)[4]) {
+    if (BYTES == 2) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(raw + kPadWords + i0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            L[q] = (int32_t)prmt(w[q], 0, 0x9910);
+            R[q] = (int32_t)prmt(w[q], 0, 0xBB32);
+        }
+    } else {
+        const uint2 *p = reinterpret_cast<const uint2 *>(raw + kPadWords + (i0 * 6) / 4);  // 24 bytes, 8-byte aligned
+        const uint2 v0 = p[0], v1 = p[1], v2 = p[2];
+        const uint32_t w[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t a = w[3 * k], b = w[3 * k + 1], d = w[3 * k + 2];
             L[2 * k] = (int32_t)prmt(a, b, 0xA210);
             R[2 * k] = (int32_t)prmt(a, b, 0xD543);
             L[2 * k + 1] = (int32_t)prmt(b, d, 0xC432);
@@ -108,60 +178,25 @@ ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (
     }
 }
 
-// candidate channel SLOT of a stereo frame: 0 L, 1 R, 2 M = (L + R) >> 1, 3 S = L - R (encoder.zig:330-350)
-template <int SLOT>
-ZF_DEVICE void make_x(const int32_t (&L)[kXn], const int32_t (&R)[kXn], int32_t (&x)[kXn]) {
-#pragma unroll
-    for (int i = 0; i < kXn; i++) {
-        if (SLOT == 0) x[i] = L[i];
-        else if (SLOT == 1) x[i] = R[i];
-        else if (SLOT == 2) x[i] = (L[i] + R[i]) >> 1;
-        else x[i] = L[i] - R[i];
-    }
-}
+// fixed.bestOrder's difference chain for one candidate channel, streamed four samples at a time
+struct Chain {
+    int32_t xp, e1p, e2p, e3p;        // previous sample and differences
+    uint32_t s0, s1, s2, s3, s4, orv;  // sum |delta^k x|, OR of the samples
 
-struct P1 {
-    uint32_t s[5];
-    uint32_t orv;
-};
-
-// fixed.bestOrder (fixed.zig:85-167) on a 16-sample window: sum |delta^k x| for k = 0..4, and the OR of the samples
-// (calcWasteBits, encoder.zig:556-570).  total[k] only counts i >= k (fixed.zig:102-127): thread 0 takes its
-// first terms out again (its history is zero, so the terms are what the chain below produced).
-ZF_DEVICE void pass1(const int32_t (&x)[kXn], int t, P1 &p) {
-    const int32_t d32 = x[3] - x[2], d21 = x[2] - x[1], d10 = x[1] - x[0];
-    int32_t e1p = d32, e2p = d32 - d21, e3p = (d32 - d21) - (d21 - d10);
-    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, orv = 0;
-#pragma unroll
-    for (int j = 0; j < kS; j++) {
-        const int32_t e0 = x[kH + j];
-        const int32_t e1 = e0 - x[kH + j - 1];
+    ZF_DEVICE void init() { xp = e1p = e2p = e3p = 0; s0 = s1 = s2 = s3 = s4 = orv = 0; }
+    template <bool ACC>
+    ZF_DEVICE void step(int32_t x) {
+        const int32_t e1 = x - xp;
         const int32_t e2 = e1 - e1p;
         const int32_t e3 = e2 - e2p;
         const int32_t e4 = e3 - e3p;
-        e1p = e1; e2p = e2; e3p = e3;
-        orv |= (uint32_t)e0;
-        s0 += uabs(e0); s1 += uabs(e1); s2 += uabs(e2); s3 += uabs(e3); s4 += uabs(e4);
-    }
-    if (t == 0) {
-        int32_t f1p = 0, f2p = 0, f3p = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int32_t e0 = x[kH + j];
-            const int32_t e1 = e0 - x[kH + j - 1];
-            const int32_t e2 = e1 - f1p;
-            const int32_t e3 = e2 - f2p;
-            const int32_t e4 = e3 - f3p;
-            f1p = e1; f2p = e2; f3p = e3;
-            if (j < 1) s1 -= uabs(e1);
-            if (j < 2) s2 -= uabs(e2);
-            if (j < 3) s3 -= uabs(e3);
-            s4 -= uabs(e4);
+        xp = x; e1p = e1; e2p = e2; e3p = e3;
+        if (ACC) {
+            orv |= (uint32_t)x;
+            s0 += uabs(x); s1 += uabs(e1); s2 += uabs(e2); s3 += uabs(e3); s4 += uabs(e4);
         }
     }
-    p.s[0] = s0; p.s[1] = s1; p.s[2] = s2; p.s[3] = s3; p.s[4] = s4;
-    p.orv = orv;
-}
+};
 
 // `order` passes of in-place differencing: afterwards x[i] is the order-th difference for i >= order
 ZF_DEVICE void diff_in_place(int32_t (&x)[kXn], uint32_t order) {
@@ -172,15 +207,6 @@ ZF_DEVICE void diff_in_place(int32_t (&x)[kXn], uint32_t order) {
             for (int i = kXn - 1; i > k; i--) x[i] -= x[i - 1];
         }
     }
-}
-
-ZF_DEVICE uint32_t sel5(const uint32_t (&v)[5], uint32_t k) {
-    uint32_t r = v[0];
-    r = k == 1 ? v[1] : r;
-    r = k == 2 ? v[2] : r;
-    r = k == 3 ? v[3] : r;
-    r = k == 4 ? v[4] : r;
-    return r;
 }
 
 // rice.calcOptimalParams for one partition (rice.zig:343-395, flacCalcPartSize :402-405) in closed form, as
@@ -207,10 +233,34 @@ ZF_DEVICE void best_param_nw(unsigned long long S, uint32_t B, uint32_t n, uint3
     choice = ch;
     cost = best;
 }
+// the same for abs-sums below 2^32 (every leaf; every node of ordinary audio)
+ZF_DEVICE void best_param_32(uint32_t S, uint32_t B, uint32_t n, uint32_t P, uint32_t &choice, uint32_t &cost) {
+    uint32_t best = 5u + B * n;
+    uint32_t ch = 0x80u | B;
+    const uint32_t n2 = 2u * n;
+    uint32_t q = 0;
+    if (S > n2) {
+        q = bitlen32(S) - bitlen32(n2);
+        if ((S >> q) > n2) q++;
+    }
+    uint32_t p = q + 1u;
+    if (p > P - 1u) p = P - 1u;
+    const uint32_t sh = S >> (p - 1u);
+    const uint32_t sh32 = sh > 0x3fffffffu ? 0x3fffffffu : sh;
+    uint32_t cc = (1u + p) * n + sh32 - (n >> 1);
+    uint32_t cand = p;
+    const uint32_t c0 = S > 0x0fffffffu ? 0x7fffffffu : n + 2u * S;
+    if (c0 <= cc) { cc = c0; cand = 0; }
+    if (cc < best) { best = cc; ch = cand; }
+    choice = ch;
+    cost = best;
+}
 
 // ---- bit writer: right-aligned 64-bit shift register ------------------------------------------------------------
-// Branch-free: the flush is a predicated shared-memory reduction (the bit buffer is zeroed, so OR == store, and the
-// first/last words a thread touches may be shared with its neighbours).
+// Branch-free.  A completed 32-bit word is written with a plain predicated store: exactly one thread completes a
+// given word (the one whose bit range crosses the word's end), and it holds every bit of the word that lies in its
+// own range while the bits in front of its range are still zero in its register.  What precedes (the tail of the
+// previous thread, the frame header) is ORed into the word after a barrier (or_tail()).
 struct BitW {
 #ifdef ZF_HOST_EMU
     uint32_t *wp;
@@ -236,7 +286,7 @@ struct BitW {
         nb += fl;
 #ifdef ZF_HOST_EMU
         if (nb >= 32u) {
-            atomicOr(wp, __funnelshift_r(lo, hi, nb - 32u));
+            *wp = __funnelshift_r(lo, hi, nb - 32u);
             wp++;
         }
 #else
@@ -245,7 +295,7 @@ struct BitW {
             "{\n"
             ".reg .pred p;\n"
             "setp.ge.u32 p, %1, 32;\n"
-            "@p red.shared.or.b32 [%0], %2;\n"
+            "@p st.shared.b32 [%0], %2;\n"
             "@p add.u32 %0, %0, 4;\n"
             "}\n"
             : "+r"(wp)
@@ -263,12 +313,16 @@ struct BitW {
         }
         put(val, q + len);
     }
-    ZF_DEVICE void finish() {
+    // the pending bits, left-aligned in their word; ORed into the buffer after the barrier that ends the stores
+    ZF_DEVICE void or_tail() const {
+        if (nb) {
+            const uint32_t w = lo << (32u - nb);
 #ifdef ZF_HOST_EMU
-        if (nb) atomicOr(wp, lo << (32u - nb));
+            atomicOr(wp, w);
 #else
-        if (nb) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wp), "r"(lo << (32u - nb)) : "memory");
+            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(wp), "r"(w) : "memory");
 #endif
+        }
     }
 };
 
@@ -285,17 +339,6 @@ ZF_DEVICE uint32_t q_mulmod(uint32_t a, uint32_t b) {  // a, b < 2^15
     return q_fold(acc);  // 29-bit product: one round suffices
 }
 
-// candidate channel `slot` (runtime, uniform over the block) of this thread's window
-template <int BYTES>
-ZF_DEVICE void load_x(const uint32_t *raw, int t, uint32_t slot, int32_t (&x)[kXn]) {
-    int32_t L[kXn], R[kXn];
-    unpack20<BYTES>(raw, t, L, R);
-    if (slot == 0) make_x<0>(L, R, x);
-    else if (slot == 1) make_x<1>(L, R, x);
-    else if (slot == 2) make_x<2>(L, R, x);
-    else make_x<3>(L, R, x);
-}
-
 // what one thread knows about the subframe it helps to write
 struct Sub {
     uint32_t kind, order, waste, bps, po, method;
@@ -309,9 +352,6 @@ struct Sub {
 // samples for VERBATIM) and returns this thread's bit count.  frame_writer.zig:269-372.
 template <int BYTES>
 ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u, uint32_t (&v)[kS]) {
-    const Dec &d = sm.dec[slot];
-    u.kind = d.kind; u.order = d.order; u.waste = d.waste; u.bps = d.bps; u.po = d.po; u.method = d.method;
-    u.depth_ch = 8u * BYTES + (slot == 3 ? 1u : 0u);
     u.choice = 0;
     u.maxq = 0;
     u.at_start = false;
@@ -349,87 +389,67 @@ ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u
     return bits + qs + cnt * (u.choice + 1u);
 }
 
-ZF_DEVICE void sub_write(uint32_t *bitbuf, const int32_t (&warm)[4], int t, const Sub &u, const uint32_t (&v)[kS], uint32_t pos) {
-    BitW bw;
-    bw.init(bitbuf, pos);
+// everything of a subframe in front of this thread's residual codes (frame_writer.zig:269-329, :341-357)
+ZF_DEVICE void sub_head(BitW &bw, const int32_t (&warm)[4], int t, const Sub &u) {
     if (u.kind == kConstant) {  // :269-279: 0x00, then the un-shifted sample at full depth
         if (t == 0) {
             bw.put(0, 8);
             bw.put((uint32_t)warm[0] & (0xffffffffu >> (32u - u.depth_ch)), u.depth_ch);
-            bw.finish();
         }
         return;
     }
-    const uint32_t smask = 0xffffffffu >> (32u - u.bps);
     if (u.kind == kVerbatim) {  // :282-301
         if (t == 0) {
             bw.put(u.waste ? 3u : 2u, 8);
             if (u.waste) bw.put(1u, u.waste);
         }
-#pragma unroll
-        for (int j = 0; j < kS; j++) bw.put(v[j] & smask, u.bps);
-        bw.finish();
         return;
     }
     const uint32_t param_len = 4u + u.method;
     if (t == 0) {  // :303-329
+        const uint32_t smask = 0xffffffffu >> (32u - u.bps);
         bw.put(((8u | u.order) << 1) | (u.waste ? 1u : 0u), 8);
         if (u.waste) bw.put(1u, u.waste);
-#pragma unroll
-        for (uint32_t k = 0; k < 4; k++)
-            if (k < u.order) bw.put((uint32_t)(warm[k] >> u.waste) & smask, u.bps);
+#pragma unroll 1
+        for (uint32_t k = 0; k < u.order; k++) bw.put((uint32_t)(warm[k] >> u.waste) & smask, u.bps);
         bw.put((u.method << 4) | u.po, 6);
     }
-    const bool esc = (u.choice & 0x80u) != 0;
     if (u.at_start) {  // :341-357
-        if (esc) {
+        if (u.choice & 0x80u) {
             bw.put(u.method ? 31u : 15u, param_len);
             bw.put(u.choice & 0x7fu, 5);
         } else {
             bw.put(u.choice, param_len);
         }
     }
-    const uint32_t jstart = (t == 0) ? u.order : 0u;
-    if (esc) {
-        const uint32_t wd = u.choice & 0x7fu;
-        if (wd) {
-            const uint32_t m = 0xffffffffu >> (32u - wd);
-#pragma unroll
-            for (int j = 0; j < kS; j++) {
-                if (j >= 4 || (uint32_t)j >= jstart) {
-                    const uint32_t r = (v[j] >> 1) ^ (0u - (v[j] & 1u));  // undo the zigzag
-                    bw.put(r & m, wd);
-                }
-            }
-        }
-    } else {
-        const uint32_t k = u.choice, one = 1u << k, m = one - 1u, len = k + 1u;
-        if (u.maxq + len <= 32u) {  // every codeword fits one 32-bit field (all but pathological partitions)
-#pragma unroll
-            for (int j = 0; j < kS; j++) {
-                const uint32_t q = v[j] >> k;
-                if (j < 4) {
-                    if ((uint32_t)j >= jstart) bw.put(one | (v[j] & m), q + len);
-                } else {
-                    bw.put(one | (v[j] & m), q + len);  // :363-372: q zeros, a one, k remainder bits
-                }
-            }
-        } else {
+}
+
+// this thread's residuals / samples, any kind (the common FIXED non-escape case of both subframes at once is
+// handled by the caller)
+ZF_DEVICE void sub_body(BitW &bw, int t, const Sub &u, const uint32_t (&v)[kS]) {
+    if (u.kind == kConstant) return;
+    // rare paths: compact code (a 4-trip loop; v[] must stay in registers, so select instead of indexing)
+    const bool verb = u.kind == kVerbatim, esc = !verb && (u.choice & 0x80u);
+    const uint32_t jstart = (t == 0 && !verb) ? u.order : 0u;
+    const uint32_t wd = verb ? u.bps : (u.choice & 0x7fu);  // raw field width of VERBATIM samples / escaped residuals
+    if ((verb || esc) && wd == 0) return;
+    const uint32_t rawmask = 0xffffffffu >> (32u - (wd ? wd : 1u));
+    const uint32_t k = u.choice & 31u, one = 1u << k, m = one - 1u, len = k + 1u;
 #pragma unroll 1
-            for (int j0 = 0; j0 < kS; j0 += 4) {
+    for (int j0 = 0; j0 < kS; j0 += 4) {
 #pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    // v[] must stay in registers: select instead of indexing
-                    uint32_t z = v[jj];
-                    z = j0 == 4 ? v[4 + jj] : z;
-                    z = j0 == 8 ? v[8 + jj] : z;
-                    z = j0 == 12 ? v[12 + jj] : z;
-                    if ((uint32_t)(j0 + jj) >= jstart) bw.put_code(z >> k, one | (z & m), len);
-                }
+        for (int jj = 0; jj < 4; jj++) {
+            uint32_t z = v[jj];
+            z = j0 == 4 ? v[4 + jj] : z;
+            z = j0 == 8 ? v[8 + jj] : z;
+            z = j0 == 12 ? v[12 + jj] : z;
+            if ((uint32_t)(j0 + jj) >= jstart) {
+                if (verb) bw.put(z & rawmask, wd);                                        // :282-301
+                else if (esc) bw.put(((z >> 1) ^ (0u - (z & 1u))) & rawmask, wd);         // :341-354, zigzag undone
+                else bw.put_code(z >> k, one | (z & m), len);                             // :363-372
             }
         }
     }
-    bw.finish();
 }
 
 ZF_DEVICE void block_scan2(uint32_t (&scan)[2][kW], int t, uint32_t a, uint32_t b, uint32_t &ex_a, uint32_t &ex_b,
@@ -457,66 +477,206 @@ ZF_DEVICE void block_scan2(uint32_t (&scan)[2][kW], int t, uint32_t a, uint32_t 
     tot_b = tb;
 }
 
-// count + scan + publish + write of one frame for the chosen channel pair (sa, sb)
+// ---- deferred epilogue -------------------------------------------------------------------------------------------
+// A finished frame stays in the bit buffer while the CTA analyses its next frame; its output offset is found in the
+// meantime by a decoupled look-back over the frame-size descriptors (128 per round, fetched by cp.async so that no
+// registers are held while a round trip to L2 is in flight), and the frame is copied out just before the bit buffer
+// is needed again.  Nobody ever waits for a predecessor that is merely a little behind.
+struct Pend {
+    uint32_t valid, fidx, fbytes, lead, fits;
+};
+
+// the few FrameJob fields the epilogue needs (a kernel parameter cannot be passed on by reference cheaply)
+struct LbArgs {
+    unsigned long long *desc;
+    unsigned long long *total_bytes;
+    unsigned int *status;
+    unsigned long long out_cap;
+    uint32_t batch_frames;
+};
+
 template <int BYTES>
-ZF_DEVICE void pack_frame(Smem<BYTES> &sm, int t, const FrameJob &job, uint32_t fidx, unsigned long long frame_number,
-                          uint32_t sa, uint32_t sb, uint32_t ch_type, uint32_t &total_bits_out, uint32_t &lead_out,
-                          bool &fits_out) {
-    uint32_t va[kS], vb[kS];
-    Sub ua, ub;
-    const uint32_t len_a = sub_count<BYTES>(sm, t, sa, ua, va);
-    const uint32_t len_b = sub_count<BYTES>(sm, t, sb, ub, vb);
-    uint32_t ex_a, ex_b, tot_a, tot_b;
-    block_scan2(sm.scan, t, len_a, len_b, ex_a, ex_b, tot_a, tot_b);
-    const uint32_t hdr_bits = 8u * header_len(frame_number, (uint32_t)kN, job.sample_rate);
-    const uint32_t total_bits = hdr_bits + tot_a + tot_b;
-    const uint32_t fbytes = (total_bits + 7u) >> 3;
-    const uint32_t lead = (16u - (fbytes & 15u)) & 15u;  // leading zero bytes: the frame ends on a 16-byte boundary
-    const bool fits = (lead + fbytes + 2u) <= (uint32_t)BitBufWords<BYTES>::value * 4u;
-    if (t == 0) {
-        const unsigned long long size = fbytes + 2u;
-        job.frame_sizes[fidx] = (uint32_t)size;
-        if (fidx == 0) st_relaxed_gpu(job.desc, kFlagPrefix | size);
-        else st_relaxed_gpu(job.desc + fidx, kFlagAggregate | size);
-        if (!fits) atomicOr(job.status, kStatusBitOverflow);
-    }
-    if (fits) {
-        const uint32_t p0 = 8u * lead;
-        if (t == kT - 1) {  // frame header + CRC-8 (frame_writer.zig:151-265, :128-141)
-            uint8_t hb[16];
-            uint32_t len = build_header(hb, frame_number, 8u * BYTES, ch_type, (uint32_t)kN, job.sample_rate);
-            uint32_t crc = 0;
-            for (uint32_t k = 0; k < len; k++) crc = sm.crc8tab[crc ^ hb[k]];
-            hb[len++] = (uint8_t)crc;
-            for (uint32_t k = 0; k < len; k++) {
-                const uint32_t b = lead + k;
-                atomicOr(&sm.bits[b >> 2], (uint32_t)hb[k] << (24u - 8u * (b & 3u)));
-            }
-        }
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ch++) {  // one copy of the writer code
-            uint32_t v[kS];
+ZF_DEVICE void lb_issue(Smem<BYTES> &sm, const LbArgs &job, int lane) {
+    const int hi = sm.lb_i | 1, base = hi - 127;
 #pragma unroll
-            for (int j = 0; j < kS; j++) v[j] = ch ? vb[j] : va[j];
-            const Sub u = ch ? ub : ua;
-            sub_write(sm.bits, sm.warm[ch ? sb : sa], t, u, v, p0 + hdr_bits + (ch ? tot_a + ex_b : ex_a));
-        }
+    for (int h = 0; h < 2; h++) {
+        const int idx = base + 64 * h + 2 * lane;
+        if (idx >= 0) cp_async16_cg(&sm.lbwin[64 * h + 2 * lane], job.desc + idx);
     }
-    total_bits_out = total_bits;
-    lead_out = lead;
-    fits_out = fits;
+    cp_async_commit();
 }
 
 template <int BYTES>
-__global__ void __launch_bounds__(kT, ZF_V3_MIN_CTAS) zf_encode_stereo_v3_kernel(const FrameJob job) {
+ZF_DEVICE void lb_done(Smem<BYTES> &sm, const LbArgs &job, int lane, const Pend &P, unsigned long long excl) {
+    if (lane == 0) {
+        const unsigned long long size = P.fbytes + 2u;
+        sm.out_off = excl;
+        sm.lb_done = 1;
+        st_relaxed_gpu(job.desc + P.fidx, kFlagPrefix | (excl + size));
+        if (P.fidx + 1 == job.batch_frames) *job.total_bytes = excl + size;
+        if (excl + size > job.out_cap) atomicOr(job.status, kStatusOutOverflow);
+    }
+    __syncwarp();
+}
+
+// warp 0: begin the look-back of the pending frame
+template <int BYTES>
+ZF_NOINLINE void lb_start(Smem<BYTES> &sm, const LbArgs job, int lane, const Pend P) {
+    if (P.fidx == 0) {
+        lb_done(sm, job, lane, P, 0);
+        return;
+    }
+    if (lane == 0) {
+        sm.lb_i = (int32_t)P.fidx - 1;
+        sm.lb_excl = 0;
+        sm.lb_done = 0;
+    }
+    __syncwarp();
+    lb_issue(sm, job, lane);
+}
+
+// warp 0: take the round that is in flight (waits for it if it has not landed), start the next one if needed
+template <int BYTES>
+ZF_NOINLINE void lb_step(Smem<BYTES> &sm, const LbArgs job, int lane, const Pend P) {
+    cp_async_wait_all();
+    __syncwarp();
+    const int i = sm.lb_i;
+    const int hi = i | 1, base = hi - 127;
+    unsigned long long sum = 0;
+    bool found = false, invalid = false;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int idx = hi - 4 * lane - j;  // j = 0 is the nearest one
+        if (!found && !invalid && idx <= i) {
+            const unsigned long long d = idx < 0 ? kFlagPrefix : sm.lbwin[idx - base];
+            const uint32_t flag = (uint32_t)(d >> 62);
+            if (flag == 0u) invalid = true;
+            else {
+                sum += d & kValueMask;
+                found = flag == 2u;
+            }
+        }
+    }
+    const uint32_t pmask = __ballot_sync(0xffffffffu, found);
+    const uint32_t imask = __ballot_sync(0xffffffffu, invalid);
+    const uint32_t first_p = pmask ? ctz32(pmask) : 32u;
+    const uint32_t need = first_p >= 31u ? 0xffffffffu : ((2u << first_p) - 1u);
+    const unsigned long long tot = warp_sum(((uint32_t)lane <= first_p) ? sum : 0ull);
+    const unsigned long long excl = sm.lb_excl + tot;
+    __syncwarp();  // every lane has read the window and the state
+    if (imask & need) {  // a predecessor has not published its size yet: fetch the same window again
+        lb_issue(sm, job, lane);
+        return;
+    }
+    if (first_p < 32u) {
+        lb_done(sm, job, lane, P, excl);
+        return;
+    }
+    if (lane == 0) {
+        sm.lb_excl = excl;
+        sm.lb_i = base - 1;
+    }
+    __syncwarp();
+    lb_issue(sm, job, lane);
+}
+
+// all threads: copy the pending frame to its place in the output stream (byte-shifted, 16-byte coalesced stores);
+// the CRC-16 is assembled from the per-warp partials and goes straight to global memory
+template <int BYTES>
+ZF_NOINLINE void copy_out(const Smem<BYTES> &sm, uint8_t *out, unsigned long long out_cap, int t, const Pend P) {
+    const unsigned long long off = sm.out_off;
+    const uint32_t fbytes = P.fbytes, lead = P.lead, size = fbytes + 2u;
+    if (!P.fits || off + size > out_cap) return;
+    uint8_t *dst = out + off;
+    const uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    const uint32_t h = head < fbytes ? head : fbytes;
+    if ((uint32_t)t < h) {
+        const uint32_t b = lead + (uint32_t)t;
+        dst[t] = (uint8_t)(sm.bits[b >> 2] >> (24u - 8u * (b & 3u)));
+    }
+    const uint32_t nq = (fbytes - h) >> 4;
+    uint4 *dq = reinterpret_cast<uint4 *>(dst + h);
+    const uint32_t o = lead + h, w0 = o >> 2, sh = 8u * (o & 3u);
+    for (uint32_t k = t; k < nq; k += kT) {
+        const uint32_t *p = sm.bits + w0 + 4u * k;
+        const uint32_t b0 = p[0], b1 = p[1], b2 = p[2], b3 = p[3], b4 = p[4];
+        uint4 v;
+        v.x = prmt(__funnelshift_l(b1, b0, sh), 0, 0x0123);
+        v.y = prmt(__funnelshift_l(b2, b1, sh), 0, 0x0123);
+        v.z = prmt(__funnelshift_l(b3, b2, sh), 0, 0x0123);
+        v.w = prmt(__funnelshift_l(b4, b3, sh), 0, 0x0123);
+        dq[k] = v;
+    }
+    const uint32_t done = h + (nq << 4);
+    const uint32_t rem = fbytes - done;  // < 16
+    if ((uint32_t)t < rem) {
+        const uint32_t b = lead + done + (uint32_t)t;
+        dst[done + t] = (uint8_t)(sm.bits[b >> 2] >> (24u - 8u * (b & 3u)));
+    }
+    if (t == kT - 1) {  // CRC-16 big-endian after the padded frame (frame_writer.zig:144-148)
+        uint32_t a = 0, par = 0;
+#pragma unroll
+        for (int w = 0; w < kW; w++) { a ^= sm.crc_part[w]; par ^= sm.par_part[w]; }
+        a = q_fold((a << 2) ^ (a << 1));  // * x^16 = x^2 + x  (mod x^15 + x + 1)
+        const uint32_t flip = ((uint32_t)__popc(a) ^ (uint32_t)__popc(par)) & 1u;
+        const uint32_t crc = a ^ (flip ? 0x8003u : 0u);  // CRT with the parity (mod x + 1)
+        dst[fbytes] = (uint8_t)(crc >> 8);
+        dst[fbytes + 1] = (uint8_t)crc;
+    }
+}
+
+template <int BYTES>
+ZF_DEVICE void zero_bits(Smem<BYTES> &sm, int t, const Pend &P) {
+    uint4 *bz = reinterpret_cast<uint4 *>(sm.bits);
+    const uint4 z = {0, 0, 0, 0};
+    const uint32_t nwords = (P.lead + P.fbytes) >> 2;
+    const uint32_t n4 = P.fits ? ((nwords + 2u + 3u) >> 2) : (uint32_t)(BitBufWords<BYTES>::value + 8) / 4u;
+    for (uint32_t k = t; k < n4; k += kT) bz[k] = z;
+}
+
+// Frame header (frame_writer.zig:151-265) + CRC-8 (:128-141), one byte per lane of one warp.  Covers what this kernel
+// is launched for: block size 4096 (code 12, no trailer), a sample rate from the table (codes 1..11, no trailer),
+// frame numbers below 2^31.  Returns this lane's byte; `len` is the header length including the CRC-8.
+ZF_DEVICE uint32_t header_byte(const uint8_t *crc8tab, int lane, unsigned long long frame_number, uint32_t depth,
+                               uint32_t ch_type, uint32_t rate_code_v, uint32_t &len) {
+    const uint32_t fn = (uint32_t)frame_number;
+    // UTF-8-like number coder (:235-251): i continuation bytes of 6 bits, lowest group last
+    const uint32_t i = fn < 0x80u ? 0u : fn < 0x800u ? 1u : fn < 0x10000u ? 2u : fn < 0x200000u ? 3u : fn < 0x4000000u ? 4u : 5u;
+    len = 4u + 1u + i + 1u;
+    const uint32_t dc = depth == 16 ? 8u : 12u;  // :221-233
+    uint32_t b = 0;
+    const uint32_t k = (uint32_t)lane;
+    if (k == 0) b = 0xFFu;
+    else if (k == 1) b = 0xF8u;  // fixed-blocksize stream, :163
+    else if (k == 2) b = (12u << 4) | rate_code_v;
+    else if (k == 3) b = (ch_type << 4) | dc;
+    else if (k == 4) b = i == 0 ? fn : (((0xFEu << (6u - i)) | (fn >> (6u * i))) & 0xFFu);
+    else if (k <= 4u + i) {
+        const uint32_t gi = 4u + i - k;  // group index, 0 = least significant
+        b = 0x80u + ((fn >> (6u * gi)) & 0x3fu);
+        if (gi == 4u) b &= 0x0Fu;  // u36 shift truncation in the reference for numbers >= 2^26
+    }
+    // CRC-8 (poly 0x07, init 0) is linear: byte k contributes T^(len-1-k)[byte], T = one table step
+    uint32_t v = (k < len - 1u) ? b : 0u;
+    const uint32_t steps = len - 1u - (k < len - 1u ? k : len - 1u);
+    for (uint32_t r = 0; r < 10u; r++)
+        if (r < steps) v = crc8tab[v];
+    const uint32_t crc = reduce_xor(v);
+    if (k == len - 1u) b = crc;
+    return b;
+}
+
+template <int BYTES>
+__global__ void __launch_bounds__(kT, kCtasPerSm) zf_encode_stereo_v3_kernel(const FrameJob job) {
     extern __shared__ __align__(16) unsigned char zf_smem[];
     Smem<BYTES> &sm = *reinterpret_cast<Smem<BYTES> *>(zf_smem);
+    Scratch &sc = sm.sc;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     constexpr uint32_t depth = 8u * BYTES;
     constexpr uint32_t frame_bytes = (uint32_t)kN * 2u * BYTES;
     const bool tma = job.use_tma != 0;
 
-    {   // once per CTA: CRC-8 table, zero pad and bit buffer, barrier, first frame
+    {   // once per CTA: CRC-8 table, zero pad, bit buffer and level partials, barrier, first frame
         uint32_t v8 = (uint32_t)t;
 #pragma unroll
         for (int k = 0; k < 8; k++) v8 = (v8 & 0x80u) ? ((v8 << 1) ^ 0x07u) : (v8 << 1);
@@ -525,13 +685,17 @@ __global__ void __launch_bounds__(kT, ZF_V3_MIN_CTAS) zf_encode_stereo_v3_kernel
         uint4 *bz = reinterpret_cast<uint4 *>(sm.bits);
         const uint4 z = {0, 0, 0, 0};
         for (int k = t; k < (BitBufWords<BYTES>::value + 8) / 4; k += kT) bz[k] = z;
+        for (int k = t; k < 4 * 9 * 16; k += kT) {
+            (&sm.lvlcost[0][0][0])[k] = 0;
+            (&sm.lvlfive[0][0][0])[k] = 0;
+        }
         if (t == 0) {
             if (tma) {
                 mbar_init(&sm.mbar, 1);
                 fence_mbar_init();
             }
             const uint32_t f = atomicAdd(job.ticket, 1u);
-            sm.cur_frame = f;
+            sm.next_frame = f;
             if (tma && f < job.n_frames) {
                 mbar_expect_tx(&sm.mbar, frame_bytes);
                 tma_load_1d(sm.raw + kPadWords, job.pcm + (size_t)f * job.frame_stride, frame_bytes, &sm.mbar);
@@ -540,10 +704,14 @@ __global__ void __launch_bounds__(kT, ZF_V3_MIN_CTAS) zf_encode_stereo_v3_kernel
     }
     __syncthreads();
     uint32_t phase = 0;
+    uint32_t f = sm.next_frame;
+    LbArgs lba;
+    lba.desc = job.desc; lba.total_bytes = job.total_bytes; lba.status = job.status; lba.out_cap = job.out_cap;
+    lba.batch_frames = job.batch_frames;
+    Pend P;
+    P.valid = 0; P.fidx = 0; P.fbytes = 0; P.lead = 0; P.fits = 0;
 
-    for (;;) {
-        const uint32_t f = sm.cur_frame;
-        if (f >= job.n_frames) break;
+    while (f < job.n_frames) {
         const uint32_t fidx = job.frame_base + f;
         const unsigned long long frame_number = job.first_frame_number + fidx;
         if (tma) {
@@ -561,56 +729,108 @@ __global__ void __launch_bounds__(kT, ZF_V3_MIN_CTAS) zf_encode_stereo_v3_kernel
             __syncthreads();
         }
 
-        // ================= pass 1: four candidates, sums kept in registers =================
-        uint32_t ks[4][5];
+        // ================= pass 1: the four candidates =================
+        // fixed.bestOrder (fixed.zig:85-167) + calcWasteBits' OR (encoder.zig:556-570), streamed: five trips over one
+        // piece of code, four inter-channel samples per trip (the first trip runs the chains over the history only),
+        // all four candidate channels L, R, M = (L + R) >> 1, S = L - R side by side.
         {
-            int32_t L[kXn], R[kXn];
-            unpack20<BYTES>(sm.raw, t, L, R);
-#define ZF3_PASS1(SLOT)                                                                     \
-    {                                                                                       \
-        int32_t x[kXn];                                                                     \
-        make_x<SLOT>(L, R, x);                                                              \
-        P1 p;                                                                               \
-        pass1(x, t, p);                                                                     \
-        if (t == 0) {                                                                       \
-            _Pragma("unroll") for (int k = 0; k < 4; k++) sm.warm[SLOT][k] = x[kH + k];     \
-        }                                                                                   \
-        _Pragma("unroll") for (int k = 0; k < 5; k++) {                                     \
-            ks[SLOT][k] = p.s[k];                                                           \
-            if (BYTES == 2) {                                                               \
-                const uint32_t ws = reduce_add(p.s[k]);                                     \
-                if (lane == 0) { sm.red[warp][SLOT][2 * k] = ws; sm.red[warp][SLOT][2 * k + 1] = 0; } \
-            } else {                                                                        \
-                const uint32_t lo = reduce_add(p.s[k] & 0xffffu), hi = reduce_add(p.s[k] >> 16); \
-                if (lane == 0) { sm.red[warp][SLOT][2 * k] = lo; sm.red[warp][SLOT][2 * k + 1] = hi; } \
-            }                                                                               \
-        }                                                                                   \
-        const uint32_t wo = reduce_or(p.orv);                                               \
-        if (lane == 0) sm.red[warp][SLOT][10] = wo;                                         \
+            Chain c0, c1, c2, c3;
+            c0.init(); c1.init(); c2.init(); c3.init();
+            {
+                int32_t L[4], R[4];
+                load4<BYTES>(sm.raw, kS * t - kH, L, R);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    c0.template step<false>(L[q]);
+                    c1.template step<false>(R[q]);
+                    c2.template step<false>((L[q] + R[q]) >> 1);
+                    c3.template step<false>(L[q] - R[q]);
+                }
+            }
+#pragma unroll 1
+            for (int g = 0; g < kS / 4; g++) {
+                int32_t L[4], R[4];
+                load4<BYTES>(sm.raw, kS * t + 4 * g, L, R);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    c0.template step<true>(L[q]);
+                    c1.template step<true>(R[q]);
+                    c2.template step<true>((L[q] + R[q]) >> 1);
+                    c3.template step<true>(L[q] - R[q]);
+                }
+            }
+            if (t == 0) {
+                // total[k] only counts i >= k (fixed.zig:102-127): take the first terms out again (the history of
+                // thread 0 is the zero pad, so the chain produced exactly these terms); keep the warm-up samples
+                int32_t L[4], R[4];
+                load4<BYTES>(sm.raw, 0, L, R);
+#define ZF3_FIX(C, SLOT, EXPR)                                                          \
+    {                                                                                   \
+        int32_t f1p = 0, f2p = 0, f3p = 0, fxp = 0;                                     \
+        _Pragma("unroll") for (int q = 0; q < 4; q++) {                                 \
+            const int32_t x = (EXPR);                                                   \
+            const int32_t e1 = x - fxp, e2 = e1 - f1p, e3 = e2 - f2p, e4 = e3 - f3p;    \
+            fxp = x; f1p = e1; f2p = e2; f3p = e3;                                      \
+            if (q < 1) C.s1 -= uabs(e1);                                                \
+            if (q < 2) C.s2 -= uabs(e2);                                                \
+            if (q < 3) C.s3 -= uabs(e3);                                                \
+            C.s4 -= uabs(e4);                                                           \
+            sm.warm[SLOT][q] = x;                                                       \
+        }                                                                               \
     }
-            ZF3_PASS1(2) ZF3_PASS1(3) ZF3_PASS1(0) ZF3_PASS1(1)
-#undef ZF3_PASS1
+                ZF3_FIX(c0, 0, L[q]) ZF3_FIX(c1, 1, R[q]) ZF3_FIX(c2, 2, (L[q] + R[q]) >> 1) ZF3_FIX(c3, 3, L[q] - R[q])
+#undef ZF3_FIX
+            }
+#define ZF3_RED(C, SLOT)                                                                         \
+    {                                                                                            \
+        uint32_t *rp = &sc.red[warp][SLOT][0];                                                   \
+        const uint32_t sv[5] = {C.s0, C.s1, C.s2, C.s3, C.s4};                                   \
+        _Pragma("unroll") for (int k = 0; k < 5; k++) {                                          \
+            if (BYTES == 2) { /* 16 x 2^20 x 32 lanes < 2^32 */                                  \
+                const uint32_t ws = reduce_add(sv[k]);                                           \
+                if (lane == 0) { rp[2 * k] = ws; rp[2 * k + 1] = 0; }                            \
+            } else {                                                                             \
+                const uint32_t lo = reduce_add(sv[k] & 0xffffu), hi = reduce_add(sv[k] >> 16);   \
+                if (lane == 0) { rp[2 * k] = lo; rp[2 * k + 1] = hi; }                           \
+            }                                                                                    \
+        }                                                                                        \
+        const uint32_t wo = reduce_or(C.orv);                                                    \
+        if (lane == 0) rp[10] = wo;                                                              \
+    }
+            ZF3_RED(c0, 0) ZF3_RED(c1, 1) ZF3_RED(c2, 2) ZF3_RED(c3, 3)
+#undef ZF3_RED
         }
         __syncthreads();
         // ---- decide (one lane per candidate): encoder.zig:482-527, fixed.zig:160-166, rice.zig:97-104 ----
-        if (warp == 0 && lane < 4) {
-            const uint32_t s = (uint32_t)lane;
-            unsigned long long tot[5];
-            uint32_t orv = 0;
+        if (warp == 0) {
+            // lane 6 s + k folds value k of candidate s over the warps (k < 5: sum |delta^k x|, k = 5: sample OR); the
+            // six values of a candidate are then exchanged inside its lane group
+            const uint32_t s = (uint32_t)lane / 6u, kk = (uint32_t)lane % 6u;
+            unsigned long long mine = 0;
+            if (lane < 24) {
+                if (kk < 5) {
+                    unsigned long long lo = 0, hi = 0;
 #pragma unroll
-            for (int k = 0; k < 5; k++) {
-                unsigned long long lo = 0, hi = 0;
+                    for (int w = 0; w < kW; w++) { lo += sc.red[w][s][2 * kk]; hi += sc.red[w][s][2 * kk + 1]; }
+                    mine = lo + (hi << 16);
+                } else {
+                    uint32_t o = 0;
 #pragma unroll
-                for (int w = 0; w < kW; w++) { lo += sm.red[w][s][2 * k]; hi += sm.red[w][s][2 * k + 1]; }
-                tot[k] = lo + (hi << 16);
+                    for (int w = 0; w < kW; w++) o |= sc.red[w][s][10];
+                    mine = o;
+                }
             }
+            unsigned long long tot[5];
 #pragma unroll
-            for (int w = 0; w < kW; w++) orv |= sm.red[w][s][10];
+            for (int k = 0; k < 5; k++) tot[k] = __shfl_sync(0xffffffffu, mine, (int)(6u * s) + k);
+            const uint32_t orv = (uint32_t)__shfl_sync(0xffffffffu, mine, (int)(6u * s) + 5);
+            if (lane < 24 && kk == 0) {
             const uint32_t depth_ch = depth + (s == 3 ? 1u : 0u);
             Dec d;
+            d.pad[0] = d.pad[1] = 0;
             d.waste = (orv == 0) ? depth_ch : ctz32(orv);
             d.bps = depth_ch - d.waste;
-            d.order = 0; d.po = 0; d.method = 0;
+            d.order = 0;
             const uint32_t lim = d.bps > 16 ? 30u : 14u;
             d.P = lim < job.max_rice_param ? lim : job.max_rice_param;
             if (d.bps == 0) {  // :495-497
@@ -633,151 +853,201 @@ __global__ void __launch_bounds__(kT, ZF_V3_MIN_CTAS) zf_encode_stereo_v3_kernel
                 d.est = (uint32_t)kN * d.bps;
             }
             sm.dec[s] = d;
+            }
         }
         __syncthreads();
 
         // ================= pass 2: leaf statistics of the chosen order, level-8 search, tree levels 7..3 ==========
         {
-            uint32_t order[4], lsum[4];
-            bool fixedk[4];
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                fixedk[s] = sm.dec[s].kind == kFixed;
-                order[s] = sm.dec[s].order;
-                lsum[s] = sel5(ks[s], order[s]);
-            }
-            int32_t L[kXn], R[kXn];
-            unpack20<BYTES>(sm.raw, t, L, R);
-#define ZF3_LEAF(SLOT)                                                                              \
-    if (fixedk[SLOT]) {                                                                             \
-        const uint32_t waste = sm.dec[SLOT].waste, P = sm.dec[SLOT].P;                              \
-        int32_t x[kXn];                                                                             \
-        make_x<SLOT>(L, R, x);                                                                      \
-        diff_in_place(x, order[SLOT]);                                                              \
-        const uint32_t jstart = (t == 0) ? order[SLOT] : 0u;                                        \
+#define ZF3_LEAF(SLOT, X)                                                                           \
+    {                                                                                               \
+        const uint32_t order = sm.dec[SLOT].order, waste = sm.dec[SLOT].waste, P = sm.dec[SLOT].P;  \
+        diff_in_place(X, order);                                                                    \
+        const uint32_t jstart = (t == 0) ? order : 0u;                                              \
         int32_t mn = 0, mx = 0;                                                                     \
+        uint32_t sum = 0;                                                                           \
         _Pragma("unroll") for (int j = 0; j < kS; j++) {                                            \
-            int32_t r = x[kH + j];                                                                  \
-            if (j < 4) r = ((uint32_t)j >= jstart) ? r : 0;                                         \
+            int32_t r = X[kH + j];                                                                  \
+            if (j < 4) r = ((uint32_t)j >= jstart) ? r : 0; /* partition 0 skips the warm-ups, rice.zig:308 */ \
+            sum += uabs(r);                                                                         \
             mn = r < mn ? r : mn;                                                                   \
             mx = r > mx ? r : mx;                                                                   \
         }                                                                                           \
         mn >>= waste;                                                                               \
         mx >>= waste;                                                                               \
         const uint32_t zm = zigzag(mn), zx = zigzag(mx);                                            \
-        uint32_t B = bitlen32(zm > zx ? zm : zx);      /* bit length of the OR of the zigzags */    \
-        unsigned long long S = lsum[SLOT] >> waste;    /* rice.calcSums, rice.zig:288-340 */        \
+        uint32_t B = bitlen32(zm > zx ? zm : zx);  /* bit length of the OR of the zigzags */        \
+        const uint32_t S32 = sum >> waste;         /* rice.calcSums, rice.zig:288-340 */            \
         uint32_t choice, cost;                                                                      \
-        best_param_nw(S, B, (uint32_t)kS - jstart, P, choice, cost);                                \
+        best_param_32(S32, B, (uint32_t)kS - jstart, P, choice, cost);                              \
         sm.choice[SLOT][256 + t] = (uint8_t)choice;                                                 \
         const uint32_t wc = reduce_add(cost);                                                       \
         const uint32_t wf = __ballot_sync(0xffffffffu, choice < 0x80u && choice > 14u);             \
-        if (lane == 0) { sm.wcostA[SLOT][warp] = wc; sm.wfiveA[SLOT][warp] = wf; }                  \
+        if (lane == 0) { sm.lvlcost[SLOT][8][warp] = wc; sm.lvlfive[SLOT][8][warp] = wf ? 1 : 0; }  \
+        unsigned long long S = S32;                                                                 \
         _Pragma("unroll") for (int lv = 7; lv >= 3; lv--) {                                         \
             const int stride = 1 << (7 - lv);                                                       \
             S += __shfl_xor_sync(0xffffffffu, S, stride);                                           \
             const uint32_t ob = __shfl_xor_sync(0xffffffffu, B, stride);                            \
             B = ob > B ? ob : B;                                                                    \
             if ((lane & (2 * stride - 1)) == 0)                                                     \
-                sm.node[SLOT][(1u << lv) + ((uint32_t)t >> (8 - lv))] = S | ((unsigned long long)B << 48); \
+                sc.node[SLOT][(1u << lv) + ((uint32_t)t >> (8 - lv))] = S | ((unsigned long long)B << 48); \
         }                                                                                           \
     }
-            ZF3_LEAF(2) ZF3_LEAF(3) ZF3_LEAF(0) ZF3_LEAF(1)
+#pragma unroll 1
+            for (uint32_t it = 0; it < 2; it++) {
+                int32_t A[kXn], B[kXn];
+                unpack20<BYTES, 0>(sm.raw, t, A, B);
+                if (it == 0) {
+#pragma unroll
+                    for (int i = 0; i < kXn; i++) {
+                        const int32_t sd = A[i] - B[i];
+                        B[i] = (A[i] + B[i]) >> 1;
+                        A[i] = sd;
+                    }
+                }
+                const uint32_t slot_a = it ? 0u : 3u, slot_b = it ? 1u : 2u;
+                if (sm.dec[slot_a].kind == kFixed) ZF3_LEAF(slot_a, A)
+                if (sm.dec[slot_b].kind == kFixed) ZF3_LEAF(slot_b, B)
+            }
 #undef ZF3_LEAF
         }
+        if (P.valid && warp == kW - 1) lb_start(sm, lba, lane, P);  // fetch the previous frame's look-back window meanwhile
         __syncthreads();
         // ================= round B: heap nodes 1..255 (levels 0..7), one per thread =================
-#pragma unroll 1
-        for (uint32_t s = 0; s < 4; s++) {
-            const Dec &d = sm.dec[s];
-            if (d.kind != kFixed) continue;
+        {
             const uint32_t m = (uint32_t)t;
-            uint32_t choice = 0, cost = 0;
-            if (m >= 1) {
-                const uint32_t lvl = floor_log2(m);
-                const uint32_t j = m - (1u << lvl);
-                unsigned long long S;
-                uint32_t B;
-                if (lvl < 3) {  // levels 2..0 straight from the eight level-3 nodes (heap 8..15)
-                    const uint32_t span = 8u >> lvl;
-                    S = 0;
-                    B = 0;
-                    for (uint32_t k = 0; k < span; k++) {
-                        const unsigned long long v = sm.node[s][8u + j * span + k];
-                        S += v & 0xffffffffffffull;
-                        const uint32_t b = (uint32_t)(v >> 48);
-                        B = b > B ? b : B;
+            const uint32_t lvl = m ? floor_log2(m) : 0u;
+            const uint32_t j = m - (1u << lvl);
+#pragma unroll 1
+            for (uint32_t s = 0; s < 4; s++) {
+                const Dec &d = sm.dec[s];
+                if (d.kind != kFixed) continue;
+                uint32_t choice = 0, cost = 0;
+                unsigned long long S = 0;
+                uint32_t B = 0;
+                if (m >= 1) {
+                    if (lvl < 3) {  // levels 2..0 straight from the eight level-3 nodes (heap 8..15): all eight are
+                                    // loaded (independent, broadcast) and the ones of this node's span are kept
+                        const ulonglong2 *np = reinterpret_cast<const ulonglong2 *>(&sc.node[s][8]);
+                        unsigned long long nv[8];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const ulonglong2 v2 = np[k];
+                            nv[2 * k] = v2.x;
+                            nv[2 * k + 1] = v2.y;
+                        }
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; k++) {
+                            const bool in = (k >> (3u - lvl)) == j;
+                            S += in ? (nv[k] & 0xffffffffffffull) : 0ull;
+                            const uint32_t b = in ? (uint32_t)(nv[k] >> 48) : 0u;
+                            B = b > B ? b : B;
+                        }
+                    } else {
+                        const unsigned long long v = sc.node[s][m];
+                        S = v & 0xffffffffffffull;
+                        B = (uint32_t)(v >> 48);
                     }
-                } else {
-                    const unsigned long long v = sm.node[s][m];
-                    S = v & 0xffffffffffffull;
-                    B = (uint32_t)(v >> 48);
                 }
                 const uint32_t cnt = ((uint32_t)kN >> lvl) - (j == 0 ? d.order : 0u);  // rice.zig:356,371
-                best_param_nw(S, B, cnt, d.P, choice, cost);
-                sm.choice[s][m] = (uint8_t)choice;
-            }
-            const bool five = m >= 1 && choice < 0x80u && choice > 14u;  // isRice2, rice.zig:74-76
-            const uint32_t fm = __ballot_sync(0xffffffffu, five);
-            if (warp == 0) {
-                sm.mixed[s][lane] = cost;
-                if (lane == 0) sm.mixfive[s] = fm;
-            } else {
-                const uint32_t wsum = reduce_add(cost);
-                if (lane == 0) { sm.wcostB[s][warp] = wsum; sm.wfiveB[s][warp] = fm; }
-            }
-        }
-        __syncthreads();
-        // ---- partition order per candidate (rice.zig:262-276: '<=' keeps the highest order on ties); FIXED needs a
-        //      strictly smaller estimate than VERBATIM (encoder.zig:538) ----
-        if (warp < 4 && sm.dec[warp].kind == kFixed) {
-            const uint32_t s = (uint32_t)warp;
-            uint32_t key = 0xffffffffu, method = 0;
-            if (lane <= 8) {
-                uint32_t cost = 0, fv = 0;
-                if (lane <= 4) {
-                    for (uint32_t m = 1u << lane; m < (2u << lane); m++) cost += sm.mixed[s][m];
-                    fv = (sm.mixfive[s] >> (1u << lane)) & ((1u << (1u << lane)) - 1u);
-                } else if (lane <= 7) {
-                    const uint32_t w0 = 1u << (lane - 5), w1 = 2u << (lane - 5);
-                    for (uint32_t w = w0; w < w1; w++) { cost += sm.wcostB[s][w]; fv |= sm.wfiveB[s][w]; }
-                } else {
-                    for (uint32_t w = 0; w < (uint32_t)kW; w++) { cost += sm.wcostA[s][w]; fv |= sm.wfiveA[s][w]; }
+                if (__any_sync(0xffffffffu, (S >> 32) != 0)) best_param_nw(S, B, cnt, d.P, choice, cost);
+                else best_param_32((uint32_t)S, B, cnt, d.P, choice, cost);
+                if (m >= 1) sm.choice[s][m] = (uint8_t)choice;
+                else cost = 0;
+                const bool five = m >= 1 && choice < 0x80u && choice > 14u;  // isRice2, rice.zig:74-76
+                const uint32_t fm = __ballot_sync(0xffffffffu, five);
+                if (warp == 0) {  // heap nodes 1..31: levels 0..4 -- each node's cost is one partial of its level
+                    if (m >= 1) {
+                        sm.lvlcost[s][lvl][j] = cost;
+                        sm.lvlfive[s][lvl][j] = five ? 1 : 0;
+                    }
+                } else {  // warp 1: level 5; warps 2-3: level 6; warps 4-7: level 7
+                    const uint32_t wsum = reduce_add(cost);
+                    const uint32_t wl = floor_log2((uint32_t)warp);
+                    if (lane == 0) {
+                        sm.lvlcost[s][5u + wl][(uint32_t)warp - (1u << wl)] = wsum;
+                        sm.lvlfive[s][5u + wl][(uint32_t)warp - (1u << wl)] = fm ? 1 : 0;
+                    }
                 }
-                method = fv ? 1u : 0u;
-                const uint32_t bc = cost + ((4u + method) << lane);  // :394
-                key = (bc << 4) | (15u - (uint32_t)lane);            // minimum cost, then the highest level
             }
-            const uint32_t bk = reduce_min(key);
-            const uint32_t bpo = 15u - (bk & 15u);
-            const uint32_t bmethod = __shfl_sync(0xffffffffu, method, (int)bpo);
-            if (lane == 0) {
-                Dec &d = sm.dec[s];
-                const uint32_t best = bk >> 4;
-                if (best < d.est) { d.est = best; d.po = bpo; d.method = bmethod; }
-                else d.kind = kVerbatim;
-            }
+        }
+        if (P.valid && warp == kW - 1) {
+            while (!sm.lb_done) lb_step(sm, lba, lane, P);
         }
         __syncthreads();
-
-        // ================= stereo mode: first minimum of [L+R, L+S, S+R, M+S], encoder.zig:441-452 =================
-        uint32_t total_bits, lead;
-        bool fits;
-        {
-            const uint32_t el = sm.dec[0].est, er = sm.dec[1].est, em = sm.dec[2].est, es = sm.dec[3].est;
-            uint32_t bestv = el + er, mode = 0;
-            if (el + es < bestv) { bestv = el + es; mode = 1; }
-            if (es + er < bestv) { bestv = es + er; mode = 2; }
-            if (em + es < bestv) { bestv = em + es; mode = 3; }
-            // Channel codes: indep(2) = 1, L/S 8, S/R 9, M/S 10 (type.zig:1-27)
-            uint32_t sa = 0, sb = 1, ch_type = 1;
-            if (mode == 1) { sb = 3; ch_type = 8; }
-            else if (mode == 2) { sa = 3; ch_type = 9; }
-            else if (mode == 3) { sa = 2; sb = 3; ch_type = 10; }
-            pack_frame<BYTES>(sm, t, job, fidx, frame_number, sa, sb, ch_type, total_bits, lead, fits);
+        if (P.valid) {  // the previous frame leaves the bit buffer
+            copy_out(sm, job.out, job.out_cap, t, P);
+            __syncthreads();
+            zero_bits(sm, t, P);  // ordered before the first stored codeword by the scan's barrier
         }
-        __syncthreads();  // all codewords placed; the raw PCM is no longer needed
+        // ---- every warp: partition order per candidate (rice.zig:262-276: '<=' keeps the highest order on ties),
+        //      FIXED only with a strictly smaller estimate than VERBATIM (encoder.zig:538), then the stereo mode:
+        //      first minimum of [L+R, L+S, S+R, M+S] (encoder.zig:441-452).  Results are uniform over the block. ----
+        Sub ua, ub;
+        uint32_t ch_type = 1, sa = 0, sb = 1;
+        {
+            uint32_t kind[4], est[4], pom[4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                kind[s] = sm.dec[s].kind;
+                est[s] = sm.dec[s].est;
+                pom[s] = 0;
+                if (kind[s] == kFixed) {
+                    uint32_t key = 0xffffffffu, method = 0;
+                    if (lane <= 8) {
+                        const uint4 *cp = reinterpret_cast<const uint4 *>(&sm.lvlcost[s][lane][0]);
+                        const uint4 c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3];
+                        const uint4 fv = *reinterpret_cast<const uint4 *>(&sm.lvlfive[s][lane][0]);
+                        const uint32_t cost = (c0.x + c0.y + c0.z + c0.w) + (c1.x + c1.y + c1.z + c1.w) +
+                                              (c2.x + c2.y + c2.z + c2.w) + (c3.x + c3.y + c3.z + c3.w);
+                        method = (fv.x | fv.y | fv.z | fv.w) ? 1u : 0u;
+                        const uint32_t bc = cost + ((4u + method) << lane);  // :394
+                        key = (bc << 4) | (15u - (uint32_t)lane);            // minimum cost, then the highest level
+                    }
+                    const uint32_t bk = reduce_min(key);
+                    const uint32_t bpo = 15u - (bk & 15u);
+                    const uint32_t bmethod = __shfl_sync(0xffffffffu, method, (int)bpo);
+                    const uint32_t best = bk >> 4;
+                    if (best < est[s]) { est[s] = best; pom[s] = bpo | (bmethod << 4); }
+                    else kind[s] = kVerbatim;
+                }
+            }
+            uint32_t bestv = est[0] + est[1], mode = 0;
+            if (est[0] + est[3] < bestv) { bestv = est[0] + est[3]; mode = 1; }
+            if (est[3] + est[1] < bestv) { bestv = est[3] + est[1]; mode = 2; }
+            if (est[2] + est[3] < bestv) { bestv = est[2] + est[3]; mode = 3; }
+            // Channel codes: indep(2) = 1, L/S 8, S/R 9, M/S 10 (type.zig:1-27)
+            uint32_t ka = kind[0], kb = kind[1], pa = pom[0], pb = pom[1];
+            if (mode == 1) { sb = 3; ch_type = 8; kb = kind[3]; pb = pom[3]; }
+            else if (mode == 2) { sa = 3; ch_type = 9; ka = kind[3]; pa = pom[3]; }
+            else if (mode == 3) { sa = 2; sb = 3; ch_type = 10; ka = kind[2]; pa = pom[2]; kb = kind[3]; pb = pom[3]; }
+            ua.kind = ka; ua.po = pa & 15u; ua.method = pa >> 4;
+            ub.kind = kb; ub.po = pb & 15u; ub.method = pb >> 4;
+            ua.order = sm.dec[sa].order; ua.waste = sm.dec[sa].waste; ua.bps = sm.dec[sa].bps;
+            ub.order = sm.dec[sb].order; ub.waste = sm.dec[sb].waste; ub.bps = sm.dec[sb].bps;
+            ua.depth_ch = depth + (sa == 3 ? 1u : 0u);
+            ub.depth_ch = depth + (sb == 3 ? 1u : 0u);
+        }
+
+        // ================= pack: count, scan, publish, write =================
+        uint32_t va[kS], vb[kS];
+        const uint32_t len_a = sub_count<BYTES>(sm, t, sa, ua, va);
+        const uint32_t len_b = sub_count<BYTES>(sm, t, sb, ub, vb);
+        uint32_t ex_a, ex_b, tot_a, tot_b;
+        block_scan2(sm.scan, t, len_a, len_b, ex_a, ex_b, tot_a, tot_b);
+        const uint32_t hdr_bits = 8u * header_len(frame_number, (uint32_t)kN, job.sample_rate);
+        const uint32_t total_bits = hdr_bits + tot_a + tot_b;
+        const uint32_t fbytes = (total_bits + 7u) >> 3;
+        const uint32_t size = fbytes + 2u;
+        const uint32_t lead = (16u - (fbytes & 15u)) & 15u;  // leading zero bytes: the frame ends on a 16-byte boundary
+        const bool fits = (lead + fbytes + 2u) <= (uint32_t)BitBufWords<BYTES>::value * 4u;
         if (t == 0) {
+            job.frame_sizes[fidx] = size;
+            if (fidx == 0) st_relaxed_gpu(job.desc, kFlagPrefix | (unsigned long long)size);
+            else st_relaxed_gpu(job.desc + fidx, kFlagAggregate | (unsigned long long)size);
+            if (!fits) atomicOr(job.status, kStatusBitOverflow);
+            // every thread has taken what it needs from the raw PCM (the scan's barrier): fetch the next frame
             const uint32_t nf = atomicAdd(job.ticket, 1u);
             sm.next_frame = nf;
             if (tma && nf < job.n_frames) {
@@ -786,40 +1056,69 @@ __global__ void __launch_bounds__(kT, ZF_V3_MIN_CTAS) zf_encode_stereo_v3_kernel
                 tma_load_1d(sm.raw + kPadWords, job.pcm + (size_t)nf * job.frame_stride, frame_bytes, &sm.mbar);
             }
         }
-
-        // ================= finish: look-back (warp 0) | CRC-16 (warps 1..7) =================
-        const uint32_t fbytes = (total_bits + 7u) >> 3;
-        const uint32_t size = fbytes + 2u;
-        const uint32_t nwords_crc = (lead + fbytes) >> 2;  // a multiple of 4: the frame ends on a 16-byte boundary
-        if (warp == 0) {
-            unsigned long long excl = 0;
-            if (fidx > 0) {
-                long long i = (long long)fidx - 1;
-                for (;;) {
-                    const long long idx = i - lane;
-                    const unsigned long long dsc = (idx >= 0) ? ld_relaxed_gpu(job.desc + idx) : kFlagPrefix;
-                    const uint32_t flag = (uint32_t)(dsc >> 62);
-                    const uint32_t pmask = __ballot_sync(0xffffffffu, flag == 2u);
-                    const uint32_t inval = __ballot_sync(0xffffffffu, flag == 0u);
-                    const uint32_t first_p = pmask ? ctz32(pmask) : 32u;
-                    const uint32_t need = first_p >= 31u ? 0xffffffffu : ((2u << first_p) - 1u);
-                    if (inval & need) continue;  // a predecessor has not published yet: poll again
-                    const unsigned long long v = ((uint32_t)lane <= first_p) ? (dsc & kValueMask) : 0ull;
-                    excl += warp_sum(v);
-                    if (first_p < 32u) break;
-                    i -= 32;
+        BitW wa, wb;
+        wa.init(sm.bits, 8u * lead + hdr_bits + ex_a);
+        wb.init(sm.bits, 8u * lead + hdr_bits + tot_a + ex_b);
+        if (fits) {
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {  // one copy of the header writer
+                BitW w = ch ? wb : wa;
+                sub_head(w, sm.warm[ch ? sb : sa], t, ch ? ub : ua);
+                if (ch) wb = w;
+                else wa = w;
+            }
+            const uint32_t lena = ua.choice + 1u, lenb = ub.choice + 1u;
+            const bool fast = ua.kind == kFixed && ub.kind == kFixed && !((ua.choice | ub.choice) & 0x80u) &&
+                              ua.maxq + lena <= 32u && ub.maxq + lenb <= 32u;
+            if (fast) {  // every codeword is one field of at most 32 bits: two independent chains, no branches
+                const uint32_t ka = ua.choice, onea = 1u << ka, ma = onea - 1u;
+                const uint32_t kb = ub.choice, oneb = 1u << kb, mb = oneb - 1u;
+                const uint32_t ja = (t == 0) ? ua.order : 0u, jb = (t == 0) ? ub.order : 0u;
+#pragma unroll
+                for (int j = 0; j < kS; j++) {  // :363-372: q zeros, a one, k remainder bits
+                    if (j < 4) {
+                        if ((uint32_t)j >= ja) wa.put(onea | (va[j] & ma), (va[j] >> ka) + lena);
+                        if ((uint32_t)j >= jb) wb.put(oneb | (vb[j] & mb), (vb[j] >> kb) + lenb);
+                    } else {
+                        wa.put(onea | (va[j] & ma), (va[j] >> ka) + lena);
+                        wb.put(oneb | (vb[j] & mb), (vb[j] >> kb) + lenb);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ch++) {  // one copy of the general writer
+                    uint32_t v[kS];
+#pragma unroll
+                    for (int j = 0; j < kS; j++) v[j] = ch ? vb[j] : va[j];
+                    BitW w = ch ? wb : wa;
+                    sub_body(w, t, ch ? ub : ua, v);
+                    if (ch) wb = w;
+                    else wa = w;
                 }
             }
-            if (lane == 0) {
-                sm.out_off = excl;
-                st_relaxed_gpu(job.desc + fidx, kFlagPrefix | (excl + size));
-                if (fidx + 1 == job.batch_frames) *job.total_bytes = excl + size;
-                if (excl + size > job.out_cap) atomicOr(job.status, kStatusOutOverflow);
+        }
+        __syncthreads();  // all complete words stored
+        if (fits) {
+            wa.or_tail();
+            wb.or_tail();
+            if (warp == kW - 1) {  // frame header, one byte per lane
+                uint32_t hlen, erb;
+                const uint32_t byte = header_byte(sm.crc8tab, lane, frame_number, depth, ch_type,
+                                                  rate_code(job.sample_rate, erb), hlen);
+                if ((uint32_t)lane < hlen) {
+                    const uint32_t b = lead + (uint32_t)lane;
+                    atomicOr(&sm.bits[b >> 2], byte << (24u - 8u * (b & 3u)));
+                }
             }
-        } else {
+        }
+        __syncthreads();
+
+        // ================= CRC-16 of the finished frame (all warps); its copy-out is deferred =================
+        {
+            const uint32_t nwords_crc = (lead + fbytes) >> 2;  // a multiple of 4: the frame ends on a 16-byte boundary
             uint32_t acc_q = 0, par = 0;
             if (fits) {
-                for (uint32_t j = (uint32_t)t - 32u; j * (uint32_t)kCrcChunkWords < nwords_crc; j += kT - 32) {
+                for (uint32_t j = (uint32_t)t; j * (uint32_t)kCrcChunkWords < nwords_crc; j += kT) {
                     const uint32_t end = nwords_crc - j * (uint32_t)kCrcChunkWords;  // exclusive
                     uint32_t a = 0;
                     if (end >= (uint32_t)kCrcChunkWords) {
@@ -840,7 +1139,7 @@ __global__ void __launch_bounds__(kT, ZF_V3_MIN_CTAS) zf_encode_stereo_v3_kernel
                             par ^= v;
                         }
                     }
-                    a = q_fold(a);                                                // < 2^15
+                    a = q_fold(a);                                                    // < 2^15
                     const uint32_t pw = job.pow8[j * (uint32_t)kCrcChunkWords * 4u];  // x^(8 * bytes after the chunk) mod P
                     acc_q ^= q_mulmod(a, q_fold(pw));
                 }
@@ -849,52 +1148,16 @@ __global__ void __launch_bounds__(kT, ZF_V3_MIN_CTAS) zf_encode_stereo_v3_kernel
             par = reduce_xor(par);
             if (lane == 0) { sm.crc_part[warp] = acc_q; sm.par_part[warp] = par; }
         }
-        __syncthreads();
-        // ---- copy-out: byte-shifted, word-coalesced; the CRC-16 goes straight to global memory ----
-        {
-            const unsigned long long off = sm.out_off;
-            if (fits && off + size <= job.out_cap) {
-                uint8_t *dst = job.out + off;
-                const uint32_t head = (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u);
-                const uint32_t h = head < fbytes ? head : fbytes;
-                if ((uint32_t)t < h) {
-                    const uint32_t b = lead + (uint32_t)t;
-                    dst[t] = (uint8_t)(sm.bits[b >> 2] >> (24u - 8u * (b & 3u)));
-                }
-                const uint32_t nw = (fbytes - h) >> 2;
-                uint32_t *dw = reinterpret_cast<uint32_t *>(dst + h);
-                const uint32_t o = lead + h, w0 = o >> 2, sh = 8u * (o & 3u);
-                for (uint32_t k = t; k < nw; k += kT) {
-                    const uint32_t be = __funnelshift_l(sm.bits[w0 + k + 1], sm.bits[w0 + k], sh);
-                    dw[k] = prmt(be, 0, 0x0123);
-                }
-                const uint32_t done = h + (nw << 2);
-                const uint32_t rem = fbytes - done;  // < 4
-                if ((uint32_t)t < rem) {
-                    const uint32_t b = lead + done + (uint32_t)t;
-                    dst[done + t] = (uint8_t)(sm.bits[b >> 2] >> (24u - 8u * (b & 3u)));
-                }
-                if (t == kT - 1) {  // CRC-16 big-endian after the padded frame (frame_writer.zig:144-148)
-                    uint32_t a = 0, par = 0;
-#pragma unroll
-                    for (int w = 1; w < kW; w++) { a ^= sm.crc_part[w]; par ^= sm.par_part[w]; }
-                    a = q_fold((a << 2) ^ (a << 1));  // * x^16 = x^2 + x  (mod x^15 + x + 1)
-                    const uint32_t flip = ((uint32_t)__popc(a) ^ (uint32_t)__popc(par)) & 1u;
-                    const uint32_t crc = a ^ (flip ? 0x8003u : 0u);  // CRT with the parity (mod x + 1)
-                    dst[fbytes] = (uint8_t)(crc >> 8);
-                    dst[fbytes + 1] = (uint8_t)crc;
-                }
-            }
+        P.valid = 1; P.fidx = fidx; P.fbytes = fbytes; P.lead = lead; P.fits = fits ? 1u : 0u;
+        f = sm.next_frame;  // written before the last two barriers
+    }
+    if (P.valid) {  // the CTA's last frame
+        if (warp == 0) {
+            lb_start(sm, lba, lane, P);
+            while (!sm.lb_done) lb_step(sm, lba, lane, P);
         }
         __syncthreads();
-        {   // zero what this frame used of the bit buffer
-            uint4 *bz = reinterpret_cast<uint4 *>(sm.bits);
-            const uint4 z = {0, 0, 0, 0};
-            const uint32_t n4 = fits ? ((nwords_crc + 2u + 3u) >> 2) : (uint32_t)(BitBufWords<BYTES>::value + 8) / 4u;
-            for (uint32_t k = t; k < n4; k += kT) bz[k] = z;
-        }
-        if (t == 0) sm.cur_frame = sm.next_frame;
-        __syncthreads();
+        copy_out(sm, job.out, job.out_cap, t, P);
     }
 }
 
