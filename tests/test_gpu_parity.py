@@ -159,3 +159,32 @@ def test_whole_file_driver(zf, oracle):
         assert got == ref
         d = oracle.decode(got)
         assert d["rc"] == 0 and d["md5_ok"] == 1
+
+
+@pytest.mark.parametrize("bits,rate", [(16, 44100), (24, 96000)])
+def test_long_single_batch_all_ctas(zf, oracle, bits, rate):
+    """One launch with many more frames than resident CTAs (3 per SM): the persistent loop, the deferred epilogue and
+    its cp.async look-back run with every CTA in flight; frames must come out in order, byte for byte."""
+    n = 4096 * 3000 + 1234
+    pcm = zf.synth_pcm(n, rate, bits)
+    with zf.Encoder(zf.Config.default(2, bits), rate, max_frames_per_batch=3001) as enc:
+        got, sizes = enc.encode_pcm(pcm, n, 77)
+        got2, sizes2 = enc.encode_pcm(pcm, n, 77)  # and again on the warm handle: no state may leak between launches
+    ref, ref_sizes = oracle.encode_pcm(pcm, n, oracle.config(2, bits), rate, 77, threads=8)
+    assert np.array_equal(sizes, ref_sizes) and np.array_equal(sizes2, ref_sizes)
+    assert got.tobytes() == ref.tobytes()
+    assert got2.tobytes() == ref.tobytes()
+
+
+def test_pageable_and_pinned_host_buffers_agree(zf, oracle):
+    """zf_encode_pcm stages pageable caller memory through pinned buffers; the three-stage pipeline
+    (upload | encode | download) must give the same bytes either way and for any batch size."""
+    bits, rate = 24, 96000
+    n = 4096 * 37 + 100
+    pcm = zf.synth_pcm(n, rate, bits)
+    ref, ref_sizes = oracle.encode_pcm(pcm, n, oracle.config(2, bits), rate, threads=8)
+    for per in (1, 2, 5, 16, 64):
+        with zf.Encoder(zf.Config.default(2, bits), rate, max_frames_per_batch=per) as enc:
+            got, sizes = enc.encode_pcm(pcm, n)
+        assert np.array_equal(sizes, ref_sizes), per
+        assert got.tobytes() == ref.tobytes(), per

@@ -34,6 +34,7 @@ thread_local char g_cuda_err[256] = "";
     } while (0)
 
 constexpr int kPow8Len = 1 << 18;
+constexpr int kSlots = 3;  // upload of batch b+1, kernels of batch b and download of batch b-1 overlap
 constexpr int kRing = 256;  // covers the largest frame of the multi-channel path (8 ch x 4096 x 33 bits)
 
 struct Slot {  // one in-flight batch: device buffers + pinned staging
@@ -57,7 +58,10 @@ struct Slot {  // one in-flight batch: device buffers + pinned staging
     uint32_t kev_count = 0;           // pairs recorded since the last zf_kernel_times()
     size_t pcm_cap = 0, out_cap = 0;
     uint32_t frames = 0;  // frames of the batch in flight
-    bool busy = false;
+    bool busy = false;      // kernels submitted, results not fetched yet
+    bool draining = false;  // output copy in flight
+    uint8_t *copy_dst = nullptr;  // pageable destination of the staged output copy
+    size_t copy_len = 0;
     bool have_io = false;
 };
 
@@ -69,8 +73,7 @@ struct zf_encoder {
     int launches_last = 0;
     float kernel_ms_last = 0.f;
     uint16_t *d_pow8 = nullptr;
-    Slot slot[2];
-    int next_slot = 0;  // submit/collect use slot 0 only; zf_encode_pcm ping-pongs
+    Slot slot[kSlots];  // submit/collect use slot 0 only; zf_encode_pcm rotates through all of them
     size_t frame_pcm_bytes = 0;
     size_t max_frame_bytes = 0;
     bool stereo = false;
@@ -365,9 +368,9 @@ int slot_submit(zf_encoder *e, Slot &sl, const uint8_t *pcm, uint64_t samples, u
     return ZF_OK;
 }
 
-// Wait for the batch, then bring exactly the produced bytes back.
-int slot_collect(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *out_len, uint32_t *frame_sizes,
-                 uint32_t frame_sizes_cap, uint32_t *n_frames) {
+// Wait for the batch's kernels, check the status, and start the copy of exactly the produced bytes (asynchronous).
+int slot_fetch(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *out_len, uint32_t *frame_sizes,
+               uint32_t frame_sizes_cap, uint32_t *n_frames) {
     if (!sl.busy) return ZF_ERR_INVALID_ARG;
     sl.busy = false;
     ZF_CUDA(cudaEventSynchronize(sl.ev_done));
@@ -385,17 +388,35 @@ int slot_collect(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *
     if (sl.frames > frame_sizes_cap) return ZF_ERR_OUT_TOO_SMALL;
     if (total > out_cap) return ZF_ERR_OUT_TOO_SMALL;
     if (frame_sizes) memcpy(frame_sizes, sl.h_sizes, sizeof(uint32_t) * sl.frames);
+    sl.copy_dst = nullptr;
+    sl.copy_len = 0;
     if (total) {
         if (is_pinned_or_device_visible(out)) {
             ZF_CUDA(cudaMemcpyAsync(out, sl.d_out, total, cudaMemcpyDeviceToHost, sl.stream));
-            ZF_CUDA(cudaStreamSynchronize(sl.stream));
-        } else {
+        } else {  // pageable caller memory: through the pinned staging buffer, copied on in slot_finish
             ZF_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, sl.stream));
-            ZF_CUDA(cudaStreamSynchronize(sl.stream));
-            memcpy(out, sl.h_out, total);
+            sl.copy_dst = out;
+            sl.copy_len = total;
         }
     }
+    sl.draining = true;
     return ZF_OK;
+}
+
+// Wait until the batch's output has arrived; the slot is free afterwards.
+int slot_finish(zf_encoder *, Slot &sl) {
+    if (!sl.draining) return ZF_OK;
+    sl.draining = false;
+    ZF_CUDA(cudaStreamSynchronize(sl.stream));
+    if (sl.copy_dst && sl.copy_len) memcpy(sl.copy_dst, sl.h_out, sl.copy_len);
+    return ZF_OK;
+}
+
+int slot_collect(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *out_len, uint32_t *frame_sizes,
+                 uint32_t frame_sizes_cap, uint32_t *n_frames) {
+    int rc = slot_fetch(e, sl, out, out_cap, out_len, frame_sizes, frame_sizes_cap, n_frames);
+    if (rc) return rc;
+    return slot_finish(e, sl);
 }
 
 }  // namespace
@@ -471,8 +492,7 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     if (cudaGetDeviceProperties(&prop, cfg->device_id) != cudaSuccess) { delete e; return ZF_ERR_CUDA; }
     e->sm_count = prop.multiProcessorCount;
     rc = setup_kernels(e);
-    if (!rc) rc = slot_init(e, e->slot[0]);
-    if (!rc) rc = slot_init(e, e->slot[1]);
+    for (int i = 0; i < kSlots && !rc; i++) rc = slot_init(e, e->slot[i]);
     if (!rc) {
         std::vector<uint16_t> pw(kPow8Len);
         uint32_t v = 1;
@@ -498,8 +518,7 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
 void zf_encoder_destroy(zf_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device_id);
-    slot_free(e->slot[0]);
-    slot_free(e->slot[1]);
+    for (int i = 0; i < kSlots; i++) slot_free(e->slot[i]);
     cudaFree(e->d_pow8);
     delete e;
 }
@@ -521,7 +540,8 @@ int zf_encode_collect(zf_encoder *e, uint8_t *out, size_t out_cap, size_t *out_l
 int zf_encode_pcm(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channel, uint64_t first_frame_number, uint8_t *out,
                   size_t out_cap, size_t *out_len, uint32_t *frame_sizes, uint32_t frame_sizes_cap, uint32_t *n_frames) {
     if (!e || !out || (!pcm && samples_per_channel)) return ZF_ERR_INVALID_ARG;
-    if (e->slot[0].busy || e->slot[1].busy) return ZF_ERR_BUSY;
+    for (int i = 0; i < kSlots; i++)
+        if (e->slot[i].busy || e->slot[i].draining) return ZF_ERR_BUSY;
     ZF_CUDA(cudaSetDevice(e->cfg.device_id));
     const uint32_t bs = e->cfg.block_size;
     const uint64_t frames = (samples_per_channel + bs - 1) / bs;
@@ -534,26 +554,35 @@ int zf_encode_pcm(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channe
     size_t pos = 0;
     float ms = 0.f;
     int launches = 0;
-    // two slots ping-pong: batch i+1 uploads and encodes while batch i drains
-    for (uint64_t b = 0; b <= nbatch; b++) {
+    auto fail = [&](int rc) {
+        for (int i = 0; i < kSlots; i++) e->slot[i].busy = e->slot[i].draining = false;
+        cudaDeviceSynchronize();
+        return rc;
+    };
+    // three-stage pipeline over the slots: batch b uploads and encodes while batch b-1's output is on its way back
+    // and batch b-2's arrival is awaited
+    for (uint64_t b = 0; b < nbatch + 2; b++) {
         if (b < nbatch) {
             const uint64_t f0 = b * per;
             const uint64_t s0 = f0 * bs;
             const uint64_t ns = std::min<uint64_t>(per * bs, samples_per_channel - s0);
-            int rc = slot_submit(e, e->slot[b & 1], pcm + s0 * ic_bytes, ns, first_frame_number + f0);
-            if (rc) { e->slot[0].busy = e->slot[1].busy = false; cudaDeviceSynchronize(); return rc; }
+            int rc = slot_submit(e, e->slot[b % kSlots], pcm + s0 * ic_bytes, ns, first_frame_number + f0);
+            if (rc) return fail(rc);
             launches += e->launches_last;
         }
-        if (b >= 1) {
+        if (b >= 1 && b - 1 < nbatch) {
             const uint64_t f0 = (b - 1) * per;
             size_t got = 0;
             uint32_t nf = 0;
-            int rc = slot_collect(e, e->slot[(b - 1) & 1], out + pos, out_cap - pos, &got,
-                                  frame_sizes ? frame_sizes + f0 : nullptr, frame_sizes ? (uint32_t)(frames - f0) : 0xffffffffu,
-                                  &nf);
-            if (rc) { e->slot[0].busy = e->slot[1].busy = false; cudaDeviceSynchronize(); return rc; }
+            int rc = slot_fetch(e, e->slot[(b - 1) % kSlots], out + pos, out_cap - pos, &got,
+                                frame_sizes ? frame_sizes + f0 : nullptr, frame_sizes ? (uint32_t)(frames - f0) : 0xffffffffu, &nf);
+            if (rc) return fail(rc);
             pos += got;
             ms += e->kernel_ms_last;
+        }
+        if (b >= 2) {
+            int rc = slot_finish(e, e->slot[(b - 2) % kSlots]);
+            if (rc) return fail(rc);
         }
     }
     e->kernel_ms_last = ms;
@@ -589,7 +618,7 @@ int zf_kernel_times(zf_encoder *e, float *ms, uint32_t cap, uint32_t *n) {
     if (!e || !n) return ZF_ERR_INVALID_ARG;
     ZF_CUDA(cudaSetDevice(e->cfg.device_id));
     uint32_t got = 0;
-    for (int si = 0; si < 2; si++) {
+    for (int si = 0; si < kSlots; si++) {
         Slot &sl = e->slot[si];
         const uint32_t have = std::min<uint32_t>(sl.kev_count, kRing);
         for (uint32_t k = 0; k < have; k++) {
