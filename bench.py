@@ -325,7 +325,7 @@ def main():
             "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
-                         "kernel": ("zf::v3::zf_encode_stereo_v3_kernel<%d>" % (bits // 8)) if bits != 32 and not os.environ.get("ZF_LEGACY_KERNEL") else ("zf::zf_encode_stereo_full_kernel<%d>" % (bits // 8)),
+                         "kernel": ("zf::v3::zf_encode_stereo_v3_kernel<%d>" % (bits // 8)) if not os.environ.get("ZF_LEGACY_KERNEL") else ("zf::zf_encode_stereo_full_kernel<%d>" % (bits // 8)),
                          "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": kernel_bytes,
                          "peak_source": peak_src,
                          "note": "integer-issue bound, not HBM bound: see DESIGN.md section 4"},

@@ -122,7 +122,8 @@ static void kernel_entry(void *) {
     }
     if (g_v3) {
         if (g_bytes == 2) zf::v3::zf_encode_stereo_v3_kernel<2>(g_job);
-        else zf::v3::zf_encode_stereo_v3_kernel<3>(g_job);
+        else if (g_bytes == 3) zf::v3::zf_encode_stereo_v3_kernel<3>(g_job);
+        else zf::v3::zf_encode_stereo_v3_kernel<4>(g_job);
         return;
     }
     if (g_full) {
@@ -178,7 +179,7 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
         g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8;
         bool table = false;
         for (unsigned r : {88200u, 176400u, 192000u, 8000u, 16000u, 22050u, 24000u, 32000u, 44100u, 48000u, 96000u}) table |= r == sample_rate;
-        g_v3 = g_full && g_allow_v3 && bytes_per_sample != 4 && max_rice_param == 30 && table;
+        g_v3 = g_full && g_allow_v3 && max_rice_param == 30 && table;
         g_job = j;
         ticket = 0;
         if (g_v3) g_v3_frames += full;

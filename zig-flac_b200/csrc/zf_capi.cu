@@ -143,7 +143,7 @@ int setup_kernels(zf_encoder *e) {
     if (e->stereo) {
         if (bytes == 2) { rc = setup_stereo_kernel<2, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<2, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<2>(e, &e->occ_v3); }
         else if (bytes == 3) { rc = setup_stereo_kernel<3, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<3, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<3>(e, &e->occ_v3); }
-        else { rc = setup_stereo_kernel<4, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<4, false>(e, &e->occ_gen); }
+        else { rc = setup_stereo_kernel<4, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<4, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<4>(e, &e->occ_v3); }
     } else {
         if (bytes == 2) rc = setup_indep_kernel<2>(e, &e->occ_gen);
         else if (bytes == 3) rc = setup_indep_kernel<3>(e, &e->occ_gen);
@@ -244,7 +244,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         job.ticket = sl.d_ctl + 0;
         if (split_tail) job.batch_frames = (uint32_t)full;  // the full-frame kernel closes its own total
         // 16/24-bit with the default Rice limits: the lean 256-thread kernel (zf_kernel_v3.cuh)
-        const bool v3 = fast && e->cfg.bit_depth != 32 && e->cfg.max_rice_param == 30 && e->occ_v3 > 0 && !e->force_legacy &&
+        const bool v3 = fast && e->cfg.max_rice_param == 30 && e->occ_v3 > 0 && !e->force_legacy &&
                         table_rate(e->cfg.sample_rate);
         const int occ = v3 ? e->occ_v3 : fast ? e->occ_full : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
@@ -252,7 +252,8 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         ZF_CUDA(cudaEventRecord(sl.kev[2 * ring], s));
         if (v3) {
             if (e->cfg.bit_depth == 16) zf::v3::zf_encode_stereo_v3_kernel<2><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
-            else zf::v3::zf_encode_stereo_v3_kernel<3><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
+            else if (e->cfg.bit_depth == 24) zf::v3::zf_encode_stereo_v3_kernel<3><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
+            else zf::v3::zf_encode_stereo_v3_kernel<4><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
         } else {
             launch_one(e, fast, grid, s, job);
         }

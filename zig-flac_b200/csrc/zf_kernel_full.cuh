@@ -159,7 +159,7 @@ ZF_DEVICE void write_fixed_full(const int32_t (&r)[kSpt], const long long (&warm
 }
 
 template <int BYTES>
-__global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_full_kernel(const FrameJob job) {
+__global__ void __launch_bounds__(kThreads, BYTES == 4 ? 1 : 2) zf_encode_stereo_full_kernel(const FrameJob job) {
     constexpr bool WIDE = (BYTES == 4);
     typedef typename Ar<WIDE>::T T;
     extern __shared__ __align__(16) unsigned char zf_smem[];

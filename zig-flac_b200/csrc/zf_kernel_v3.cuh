@@ -42,7 +42,12 @@ constexpr int kN = 4096;
 constexpr int kW = kT / 32;
 constexpr int kPadWords = 8;     // 32 zero bytes in front of the PCM: history of thread 0
 constexpr int kCrcChunkWords = 16;
-constexpr int kCtasPerSm = 3;    // 80 registers, ~66 KB of shared memory each
+// resident CTAs per SM: 16/24-bit: 80 registers, ~66 KB of shared memory each; 32-bit (64-bit chains): 128 registers, ~87 KB
+template <int BYTES> struct CtasPerSm { static constexpr int value = BYTES == 4 ? 2 : 3; };
+
+// candidate-channel arithmetic: 32-bit PCM needs 33 bits for the side channel and 37 for its fourth difference
+template <int BYTES> struct Arith { typedef int32_t T; typedef uint32_t U; };
+template <> struct Arith<4> { typedef long long T; typedef unsigned long long U; };
 
 struct Dec {  // per candidate channel, after pass 1
     uint32_t kind, order, waste, bps, P, est;
@@ -50,9 +55,12 @@ struct Dec {  // per candidate channel, after pass 1
 };
 
 // scratch of the analysis phases
+template <int BYTES>
 struct Scratch {
     unsigned long long node[4][256];  // heap nodes 8..255 (levels 3..7): abs-sum | width << 48
-    uint32_t red[kW][4][12];          // pass-1 warp partials: 5 x (lo, hi) + sample OR
+    // pass-1 warp partials.  16/24-bit: 5 x (lo, hi) sums + sample OR.  32-bit: 5 x 3 sixteen-bit pieces of the sums,
+    // 5 x (lo, hi) ORs of |delta^k x| (range check, fixed.zig:160-162), (lo, hi) sample OR.
+    uint32_t red[kW][4][BYTES == 4 ? 28 : 12];
 };
 
 template <int BYTES>
@@ -61,7 +69,7 @@ struct Smem {
     alignas(16) uint32_t bits[BitBufWords<BYTES>::value + 8];
     alignas(16) uint32_t lvlcost[4][9][16];  // per candidate, per partition order: up to 16 partial cost sums
     alignas(16) uint8_t lvlfive[4][9][16];   // ... and whether a parameter > 14 occurs (5-bit method, rice.zig:383-387)
-    alignas(16) Scratch sc;
+    alignas(16) Scratch<BYTES> sc;
     alignas(16) unsigned long long lbwin[128];  // look-back window: descriptors hi-127 .. hi (fetched by cp.async)
     unsigned long long lb_excl;                // bytes of the predecessors examined so far
     int32_t lb_i;                              // nearest predecessor not examined yet
@@ -69,7 +77,7 @@ struct Smem {
     unsigned long long mbar;
     unsigned long long out_off;
     Dec dec[4];
-    int32_t warm[4][4];               // first four samples of every candidate (warm-ups, CONSTANT value)
+    long long warm[4][4];             // first four samples of every candidate (warm-ups, CONSTANT value)
     uint32_t scan[2][kW];
     uint32_t crc_part[kW], par_part[kW];
     uint32_t next_frame;
@@ -93,7 +101,16 @@ ZF_DEVICE uint32_t shl32(uint32_t v, uint32_t s) {
 // WHICH: 0 both channels, 1 left only, 2 right only (the other array is left untouched)
 template <int BYTES, int WHICH>
 ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (&R)[kXn]) {
-    if (BYTES == 2) {
+    if (BYTES == 4) {
+        // two words per inter-channel sample
+        const uint4 *p = reinterpret_cast<const uint4 *>(raw + kPadWords + 2 * (kS * t - kH));
+#pragma unroll
+        for (int k = 0; k < kXn / 2; k++) {
+            const uint4 v = p[k];
+            if (WHICH != 2) { L[2 * k] = (int32_t)v.x; L[2 * k + 1] = (int32_t)v.z; }
+            if (WHICH != 1) { R[2 * k] = (int32_t)v.y; R[2 * k + 1] = (int32_t)v.w; }
+        }
+    } else if (BYTES == 2) {
         // one word per inter-channel sample; the window starts 4 samples before 16 t
         const uint4 *p = reinterpret_cast<const uint4 *>(raw + kPadWords + kS * t - kH);
 #pragma unroll
@@ -151,11 +168,27 @@ ZF_DEVICE void load_x(const uint32_t *raw, int t, uint32_t slot, int32_t (&x)[kX
         }
     }
 }
+// 32-bit PCM: 64-bit candidates (encoder.zig:330-339)
+template <int BYTES>
+ZF_DEVICE void load_x(const uint32_t *raw, int t, uint32_t slot, long long (&x)[kXn]) {
+    int32_t L[kXn], R[kXn];
+    unpack20<BYTES, 0>(raw, t, L, R);
+#pragma unroll
+    for (int i = 0; i < kXn; i++) {
+        const long long l = L[i], r = R[i];
+        x[i] = slot == 0 ? l : slot == 1 ? r : slot == 2 ? ((l + r) >> 1) : (l - r);
+    }
+}
 
 // four consecutive inter-channel samples starting at sample index i0 (may be -4: the zero pad) of the frame in `raw`
 template <int BYTES>
 ZF_DEVICE void load4(const uint32_t *raw, int i0, int32_t (&L)[4], int32_t (&R)[4]) {
-    if (BYTES == 2) {
+    if (BYTES == 4) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(raw + kPadWords + 2 * i0);
+        const uint4 v0 = p[0], v1 = p[1];
+        L[0] = (int32_t)v0.x; R[0] = (int32_t)v0.y; L[1] = (int32_t)v0.z; R[1] = (int32_t)v0.w;
+        L[2] = (int32_t)v1.x; R[2] = (int32_t)v1.y; L[3] = (int32_t)v1.z; R[3] = (int32_t)v1.w;
+    } else if (BYTES == 2) {
         const uint4 v = *reinterpret_cast<const uint4 *>(raw + kPadWords + i0);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -198,8 +231,46 @@ struct Chain {
     }
 };
 
+// the same in 64 bits, with the OR of |delta^k x| that fixed.bestOrder's range check needs (fixed.zig:160-162)
+struct ChainW {
+    long long xp, e1p, e2p, e3p;
+    unsigned long long s0, s1, s2, s3, s4, r0, r1, r2, r3, r4, orv;
+
+    ZF_DEVICE void init() { xp = e1p = e2p = e3p = 0; s0 = s1 = s2 = s3 = s4 = r0 = r1 = r2 = r3 = r4 = orv = 0; }
+    template <bool ACC>
+    ZF_DEVICE void step(long long x) {
+        const long long e1 = x - xp;
+        const long long e2 = e1 - e1p;
+        const long long e3 = e2 - e2p;
+        const long long e4 = e3 - e3p;
+        xp = x; e1p = e1; e2p = e2; e3p = e3;
+        if (ACC) {
+            const unsigned long long a0 = uabs(x), a1 = uabs(e1), a2 = uabs(e2), a3 = uabs(e3), a4 = uabs(e4);
+            orv |= (unsigned long long)x;
+            s0 += a0; s1 += a1; s2 += a2; s3 += a3; s4 += a4;
+            r0 |= a0; r1 |= a1; r2 |= a2; r3 |= a3; r4 |= a4;
+        }
+    }
+    // sample q < 4 of the frame: total[k] and the range OR only count samples i >= k (fixed.zig:102-127)
+    template <int Q>
+    ZF_DEVICE void step_first(long long x) {
+        const long long e1 = x - xp;
+        const long long e2 = e1 - e1p;
+        const long long e3 = e2 - e2p;
+        const long long e4 = e3 - e3p;
+        xp = x; e1p = e1; e2p = e2; e3p = e3;
+        const unsigned long long a0 = uabs(x), a1 = uabs(e1), a2 = uabs(e2), a3 = uabs(e3), a4 = uabs(e4);
+        orv |= (unsigned long long)x;
+        s0 += a0; r0 |= a0;
+        if (Q >= 1) { s1 += a1; r1 |= a1; }
+        if (Q >= 2) { s2 += a2; r2 |= a2; }
+        if (Q >= 3) { s3 += a3; r3 |= a3; }
+    }
+};
+
 // `order` passes of in-place differencing: afterwards x[i] is the order-th difference for i >= order
-ZF_DEVICE void diff_in_place(int32_t (&x)[kXn], uint32_t order) {
+template <typename TT>
+ZF_DEVICE void diff_in_place(TT (&x)[kXn], uint32_t order) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if ((uint32_t)k < order) {
@@ -230,6 +301,28 @@ ZF_DEVICE void best_param_nw(unsigned long long S, uint32_t B, uint32_t n, uint3
     const uint32_t c0 = S > 0x0fffffffull ? 0x7fffffffu : n + 2u * (uint32_t)S;  // p == 0: no -(n >> 1)
     if (c0 <= cc) { cc = c0; cand = 0; }                                         // lowest p wins ties
     if (cc < best) { best = cc; ch = cand; }                                     // escape wins ties
+    choice = ch;
+    cost = best;
+}
+// 32-bit PCM: a width of 32 makes the escape invalid (rice.zig:361-366); everything else as above
+ZF_DEVICE void best_param_w(unsigned long long S, uint32_t B, uint32_t n, uint32_t P, uint32_t &choice, uint32_t &cost) {
+    uint32_t best = B <= 31u ? 5u + B * n : 0xffffffffu;
+    uint32_t ch = 0x80u | B;
+    const uint32_t n2 = 2u * n;
+    uint32_t q = 0;
+    if (S > n2) {
+        q = bitlen64(S) - bitlen32(n2);
+        if ((S >> q) > n2) q++;
+    }
+    uint32_t p = q + 1u;
+    if (p > P - 1u) p = P - 1u;
+    const unsigned long long sh = S >> (p - 1u);
+    const uint32_t sh32 = sh > 0x3fffffffull ? 0x3fffffffu : (uint32_t)sh;
+    uint32_t cc = (1u + p) * n + sh32 - (n >> 1);
+    uint32_t cand = p;
+    const uint32_t c0 = S > 0x0fffffffull ? 0x7fffffffu : n + 2u * (uint32_t)S;
+    if (c0 <= cc) { cc = c0; cand = 0; }
+    if (cc < best) { best = cc; ch = cand; }
     choice = ch;
     cost = best;
 }
@@ -345,6 +438,7 @@ struct Sub {
     uint32_t depth_ch;
     uint32_t choice;
     uint32_t maxq;  // largest unary quotient among this thread's codes
+    uint32_t vhi;   // VERBATIM samples of 33 bits (32-bit side channel): bit j = bit 32 of sample j
     bool at_start;
 };
 
@@ -354,20 +448,25 @@ template <int BYTES>
 ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u, uint32_t (&v)[kS]) {
     u.choice = 0;
     u.maxq = 0;
+    u.vhi = 0;
     u.at_start = false;
 #pragma unroll
     for (int j = 0; j < kS; j++) v[j] = 0;
     if (u.kind == kConstant) return t == 0 ? 8u + u.depth_ch : 0u;
-    int32_t x[kXn];
+    typename Arith<BYTES>::T x[kXn];
     load_x<BYTES>(sm.raw, t, slot, x);
     if (u.kind == kVerbatim) {
 #pragma unroll
-        for (int j = 0; j < kS; j++) v[j] = (uint32_t)(x[kH + j] >> u.waste);
+        for (int j = 0; j < kS; j++) {
+            const typename Arith<BYTES>::T sv = x[kH + j] >> u.waste;
+            v[j] = (uint32_t)sv;
+            if (BYTES == 4) u.vhi |= (uint32_t)(((unsigned long long)sv >> 32) & 1ull) << j;
+        }
         return (uint32_t)kS * u.bps + (t == 0 ? 8u + u.waste : 0u);
     }
     diff_in_place(x, u.order);
 #pragma unroll
-    for (int j = 0; j < kS; j++) v[j] = zigzag(x[kH + j] >> u.waste);
+    for (int j = 0; j < kS; j++) v[j] = zigzag((int32_t)(x[kH + j] >> u.waste));  // low 32 bits, fixed.zig:70-73
     const uint32_t sh = 8u - u.po;  // threads per partition = 1 << sh
     u.choice = sm.choice[slot][(1u << u.po) + ((uint32_t)t >> sh)];
     u.at_start = ((uint32_t)t & ((1u << sh) - 1u)) == 0;
@@ -390,11 +489,21 @@ ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u
 }
 
 // everything of a subframe in front of this thread's residual codes (frame_writer.zig:269-329, :341-357)
-ZF_DEVICE void sub_head(BitW &bw, const int32_t (&warm)[4], int t, const Sub &u) {
+// a field of up to 33 bits (32-bit side channel)
+ZF_DEVICE void put_wide(BitW &bw, long long value, uint32_t width) {
+    if (width > 32u) {
+        bw.put((uint32_t)((unsigned long long)value >> 32) & (0xffffffffu >> (64u - width)), width - 32u);
+        bw.put((uint32_t)value, 32);
+    } else {
+        bw.put((uint32_t)value & (0xffffffffu >> (32u - width)), width);
+    }
+}
+
+ZF_DEVICE void sub_head(BitW &bw, const long long (&warm)[4], int t, const Sub &u) {
     if (u.kind == kConstant) {  // :269-279: 0x00, then the un-shifted sample at full depth
         if (t == 0) {
             bw.put(0, 8);
-            bw.put((uint32_t)warm[0] & (0xffffffffu >> (32u - u.depth_ch)), u.depth_ch);
+            put_wide(bw, warm[0], u.depth_ch);
         }
         return;
     }
@@ -407,11 +516,10 @@ ZF_DEVICE void sub_head(BitW &bw, const int32_t (&warm)[4], int t, const Sub &u)
     }
     const uint32_t param_len = 4u + u.method;
     if (t == 0) {  // :303-329
-        const uint32_t smask = 0xffffffffu >> (32u - u.bps);
         bw.put(((8u | u.order) << 1) | (u.waste ? 1u : 0u), 8);
         if (u.waste) bw.put(1u, u.waste);
 #pragma unroll 1
-        for (uint32_t k = 0; k < u.order; k++) bw.put((uint32_t)(warm[k] >> u.waste) & smask, u.bps);
+        for (uint32_t k = 0; k < u.order; k++) put_wide(bw, warm[k] >> u.waste, u.bps);
         bw.put((u.method << 4) | u.po, 6);
     }
     if (u.at_start) {  // :341-357
@@ -433,7 +541,7 @@ ZF_DEVICE void sub_body(BitW &bw, int t, const Sub &u, const uint32_t (&v)[kS]) 
     const uint32_t jstart = (t == 0 && !verb) ? u.order : 0u;
     const uint32_t wd = verb ? u.bps : (u.choice & 0x7fu);  // raw field width of VERBATIM samples / escaped residuals
     if ((verb || esc) && wd == 0) return;
-    const uint32_t rawmask = 0xffffffffu >> (32u - (wd ? wd : 1u));
+    const uint32_t rawmask = wd >= 32u ? 0xffffffffu : (0xffffffffu >> (32u - (wd ? wd : 1u)));
     const uint32_t k = u.choice & 31u, one = 1u << k, m = one - 1u, len = k + 1u;
 #pragma unroll 1
     for (int j0 = 0; j0 < kS; j0 += 4) {
@@ -444,7 +552,14 @@ ZF_DEVICE void sub_body(BitW &bw, int t, const Sub &u, const uint32_t (&v)[kS]) 
             z = j0 == 8 ? v[8 + jj] : z;
             z = j0 == 12 ? v[12 + jj] : z;
             if ((uint32_t)(j0 + jj) >= jstart) {
-                if (verb) bw.put(z & rawmask, wd);                                        // :282-301
+                if (verb) {                                                               // :282-301
+                    if (wd > 32u) {  // 33-bit samples of the 32-bit side channel
+                        bw.put((u.vhi >> (j0 + jj)) & 1u, 1);
+                        bw.put(z, 32);
+                    } else {
+                        bw.put(z & rawmask, wd);
+                    }
+                }
                 else if (esc) bw.put(((z >> 1) ^ (0u - (z & 1u))) & rawmask, wd);         // :341-354, zigzag undone
                 else bw.put_code(z >> k, one | (z & m), len);                             // :363-372
             }
@@ -643,7 +758,7 @@ ZF_DEVICE uint32_t header_byte(const uint8_t *crc8tab, int lane, unsigned long l
     // UTF-8-like number coder (:235-251): i continuation bytes of 6 bits, lowest group last
     const uint32_t i = fn < 0x80u ? 0u : fn < 0x800u ? 1u : fn < 0x10000u ? 2u : fn < 0x200000u ? 3u : fn < 0x4000000u ? 4u : 5u;
     len = 4u + 1u + i + 1u;
-    const uint32_t dc = depth == 16 ? 8u : 12u;  // :221-233
+    const uint32_t dc = depth == 16 ? 8u : depth == 24 ? 12u : 14u;  // :221-233
     uint32_t b = 0;
     const uint32_t k = (uint32_t)lane;
     if (k == 0) b = 0xFFu;
@@ -667,10 +782,13 @@ ZF_DEVICE uint32_t header_byte(const uint8_t *crc8tab, int lane, unsigned long l
 }
 
 template <int BYTES>
-__global__ void __launch_bounds__(kT, kCtasPerSm) zf_encode_stereo_v3_kernel(const FrameJob job) {
+__global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_v3_kernel(const FrameJob job) {
     extern __shared__ __align__(16) unsigned char zf_smem[];
     Smem<BYTES> &sm = *reinterpret_cast<Smem<BYTES> *>(zf_smem);
-    Scratch &sc = sm.sc;
+    Scratch<BYTES> &sc = sm.sc;
+    constexpr bool WIDE = BYTES == 4;
+    typedef typename Arith<BYTES>::T T;
+    typedef typename Arith<BYTES>::U U;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     constexpr uint32_t depth = 8u * BYTES;
     constexpr uint32_t frame_bytes = (uint32_t)kN * 2u * BYTES;
@@ -733,6 +851,72 @@ __global__ void __launch_bounds__(kT, kCtasPerSm) zf_encode_stereo_v3_kernel(con
         // fixed.bestOrder (fixed.zig:85-167) + calcWasteBits' OR (encoder.zig:556-570), streamed: five trips over one
         // piece of code, four inter-channel samples per trip (the first trip runs the chains over the history only),
         // all four candidate channels L, R, M = (L + R) >> 1, S = L - R side by side.
+        if constexpr (WIDE) {
+            // 64-bit chains: two candidates at a time (registers), two trips over the samples
+#pragma unroll 1
+            for (uint32_t trip = 0; trip < 2; trip++) {
+                ChainW ca, cb;  // trip 0: L, R; trip 1: M, S
+                ca.init(); cb.init();
+                {
+                    int32_t L[4], R[4];
+                    load4<BYTES>(sm.raw, kS * t - kH, L, R);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const long long l = L[q], r = R[q];
+                        ca.template step<false>(trip ? ((l + r) >> 1) : l);
+                        cb.template step<false>(trip ? (l - r) : r);
+                    }
+                }
+                const uint32_t slot_a = trip ? 2u : 0u, slot_b = trip ? 3u : 1u;
+#pragma unroll 1
+                for (int g = 0; g < kS / 4; g++) {
+                    int32_t L[4], R[4];
+                    load4<BYTES>(sm.raw, kS * t + 4 * g, L, R);
+                    long long xa[4], xb[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const long long l = L[q], r = R[q];
+                        xa[q] = trip ? ((l + r) >> 1) : l;
+                        xb[q] = trip ? (l - r) : r;
+                    }
+                    if (t == 0 && g == 0) {  // the frame's first samples; they are the warm-ups too
+                        ca.template step_first<0>(xa[0]); ca.template step_first<1>(xa[1]);
+                        ca.template step_first<2>(xa[2]); ca.template step_first<3>(xa[3]);
+                        cb.template step_first<0>(xb[0]); cb.template step_first<1>(xb[1]);
+                        cb.template step_first<2>(xb[2]); cb.template step_first<3>(xb[3]);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { sm.warm[slot_a][q] = xa[q]; sm.warm[slot_b][q] = xb[q]; }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            ca.template step<true>(xa[q]);
+                            cb.template step<true>(xb[q]);
+                        }
+                    }
+                }
+#define ZF3_REDW(C, SLOT)                                                                        \
+    {                                                                                            \
+        uint32_t *rp = &sc.red[warp][SLOT][0];                                                   \
+        const unsigned long long sv[5] = {C.s0, C.s1, C.s2, C.s3, C.s4};                         \
+        const unsigned long long rv[5] = {C.r0, C.r1, C.r2, C.r3, C.r4};                         \
+        _Pragma("unroll") for (int k = 0; k < 5; k++) {                                          \
+            const uint32_t p0 = reduce_add((uint32_t)sv[k] & 0xffffu);                           \
+            const uint32_t p1 = reduce_add((uint32_t)(sv[k] >> 16) & 0xffffu);                   \
+            const uint32_t p2 = reduce_add((uint32_t)(sv[k] >> 32));  /* per-thread sums < 2^42 */ \
+            const uint32_t o0 = reduce_or((uint32_t)rv[k]), o1 = reduce_or((uint32_t)(rv[k] >> 32)); \
+            if (lane == 0) {                                                                     \
+                rp[3 * k] = p0; rp[3 * k + 1] = p1; rp[3 * k + 2] = p2;                          \
+                rp[15 + 2 * k] = o0; rp[16 + 2 * k] = o1;                                        \
+            }                                                                                    \
+        }                                                                                        \
+        const uint32_t w0 = reduce_or((uint32_t)C.orv), w1 = reduce_or((uint32_t)(C.orv >> 32)); \
+        if (lane == 0) { rp[25] = w0; rp[26] = w1; }                                             \
+    }
+                ZF3_REDW(ca, slot_a)
+                ZF3_REDW(cb, slot_b)
+#undef ZF3_REDW
+            }
+        } else
         {
             Chain c0, c1, c2, c3;
             c0.init(); c1.init(); c2.init(); c3.init();
@@ -806,29 +990,51 @@ __global__ void __launch_bounds__(kT, kCtasPerSm) zf_encode_stereo_v3_kernel(con
             // lane 6 s + k folds value k of candidate s over the warps (k < 5: sum |delta^k x|, k = 5: sample OR); the
             // six values of a candidate are then exchanged inside its lane group
             const uint32_t s = (uint32_t)lane / 6u, kk = (uint32_t)lane % 6u;
-            unsigned long long mine = 0;
+            unsigned long long mine = 0, mine_rng = 0;
             if (lane < 24) {
-                if (kk < 5) {
-                    unsigned long long lo = 0, hi = 0;
+                if constexpr (WIDE) {
+                    if (kk < 5) {
+                        unsigned long long p0 = 0, p1 = 0, p2 = 0;
+                        uint32_t o0 = 0, o1 = 0;
 #pragma unroll
-                    for (int w = 0; w < kW; w++) { lo += sc.red[w][s][2 * kk]; hi += sc.red[w][s][2 * kk + 1]; }
-                    mine = lo + (hi << 16);
+                        for (int w = 0; w < kW; w++) {
+                            p0 += sc.red[w][s][3 * kk]; p1 += sc.red[w][s][3 * kk + 1]; p2 += sc.red[w][s][3 * kk + 2];
+                            o0 |= sc.red[w][s][15 + 2 * kk]; o1 |= sc.red[w][s][16 + 2 * kk];
+                        }
+                        mine = p0 + (p1 << 16) + (p2 << 32);
+                        mine_rng = (unsigned long long)o0 | ((unsigned long long)o1 << 32);
+                    } else {
+                        uint32_t o0 = 0, o1 = 0;
+#pragma unroll
+                        for (int w = 0; w < kW; w++) { o0 |= sc.red[w][s][25]; o1 |= sc.red[w][s][26]; }
+                        mine = (unsigned long long)o0 | ((unsigned long long)o1 << 32);
+                    }
                 } else {
-                    uint32_t o = 0;
+                    if (kk < 5) {
+                        unsigned long long lo = 0, hi = 0;
 #pragma unroll
-                    for (int w = 0; w < kW; w++) o |= sc.red[w][s][10];
-                    mine = o;
+                        for (int w = 0; w < kW; w++) { lo += sc.red[w][s][2 * kk]; hi += sc.red[w][s][2 * kk + 1]; }
+                        mine = lo + (hi << 16);
+                    } else {
+                        uint32_t o = 0;
+#pragma unroll
+                        for (int w = 0; w < kW; w++) o |= sc.red[w][s][10];
+                        mine = o;
+                    }
                 }
             }
-            unsigned long long tot[5];
+            unsigned long long tot[5], rng[5];
 #pragma unroll
-            for (int k = 0; k < 5; k++) tot[k] = __shfl_sync(0xffffffffu, mine, (int)(6u * s) + k);
-            const uint32_t orv = (uint32_t)__shfl_sync(0xffffffffu, mine, (int)(6u * s) + 5);
+            for (int k = 0; k < 5; k++) {
+                tot[k] = __shfl_sync(0xffffffffu, mine, (int)(6u * s) + k);
+                rng[k] = WIDE ? __shfl_sync(0xffffffffu, mine_rng, (int)(6u * s) + k) : 0ull;
+            }
+            const unsigned long long orv = __shfl_sync(0xffffffffu, mine, (int)(6u * s) + 5);
             if (lane < 24 && kk == 0) {
             const uint32_t depth_ch = depth + (s == 3 ? 1u : 0u);
             Dec d;
             d.pad[0] = d.pad[1] = 0;
-            d.waste = (orv == 0) ? depth_ch : ctz32(orv);
+            d.waste = (orv == 0) ? depth_ch : ctz64(orv);
             d.bps = depth_ch - d.waste;
             d.order = 0;
             const uint32_t lim = d.bps > 16 ? 30u : 14u;
@@ -840,17 +1046,23 @@ __global__ void __launch_bounds__(kT, kCtasPerSm) zf_encode_stereo_v3_kernel(con
                 d.kind = kConstant;
                 d.est = d.bps;
             } else {
-                // every |delta^k x| is a multiple of 2^waste, so the shift commutes with the sums
+                // every |delta^k x| is a multiple of 2^waste, so the shift commutes with the sums (and the range ORs)
+                const bool check = WIDE && d.bps >= 28;  // "wide accumulator", encoder.zig:517-520
                 uint32_t best = 0;
-                unsigned long long bv = tot[0] >> d.waste;
+                unsigned long long bv = 0;
 #pragma unroll
-                for (uint32_t k = 1; k < 5; k++) {
-                    const unsigned long long v = tot[k] >> d.waste;
-                    if (v < bv) { bv = v; best = k; }  // first minimum, fixed.zig:164
+                for (uint32_t k = 0; k < 5; k++) {
+                    unsigned long long v = tot[k] >> d.waste;
+                    if (check && (rng[k] >> d.waste) > 0x7fffffffull) v = kU64Max;  // fixed.zig:160-162
+                    if (k == 0 || v < bv) { bv = v; best = k; }                     // first minimum, fixed.zig:164
                 }
-                d.kind = kFixed;  // tentative: FIXED only if the Rice estimate beats VERBATIM (:538)
-                d.order = best;
                 d.est = (uint32_t)kN * d.bps;
+                if (check && bv == kU64Max) {  // no usable order: VERBATIM (fixed.zig:166, encoder.zig:521-527)
+                    d.kind = kVerbatim;
+                } else {
+                    d.kind = kFixed;  // tentative: FIXED only if the Rice estimate beats VERBATIM (:538)
+                    d.order = best;
+                }
             }
             sm.dec[s] = d;
             }
@@ -894,6 +1106,45 @@ __global__ void __launch_bounds__(kT, kCtasPerSm) zf_encode_stereo_v3_kernel(con
                 sc.node[SLOT][(1u << lv) + ((uint32_t)t >> (8 - lv))] = S | ((unsigned long long)B << 48); \
         }                                                                                           \
     }
+            if constexpr (WIDE) {
+                // 64-bit residual chains, one candidate per trip; the residual itself is the low 32 bits (fixed.zig:70-73)
+#pragma unroll 1
+                for (uint32_t s = 0; s < 4; s++) {
+                    if (sm.dec[s].kind != kFixed) continue;
+                    const uint32_t order = sm.dec[s].order, waste = sm.dec[s].waste, P = sm.dec[s].P;
+                    long long x[kXn];
+                    load_x<BYTES>(sm.raw, t, s, x);
+                    diff_in_place(x, order);
+                    const uint32_t jstart = (t == 0) ? order : 0u;
+                    int32_t mn = 0, mx = 0;
+                    unsigned long long S = 0;
+#pragma unroll
+                    for (int j = 0; j < kS; j++) {
+                        int32_t r = (int32_t)(x[kH + j] >> waste);
+                        if (j < 4) r = ((uint32_t)j >= jstart) ? r : 0;  // partition 0 skips the warm-ups, rice.zig:308
+                        S += uabs(r);
+                        mn = r < mn ? r : mn;
+                        mx = r > mx ? r : mx;
+                    }
+                    const uint32_t zm = zigzag(mn), zx = zigzag(mx);
+                    uint32_t B = bitlen32(zm > zx ? zm : zx);
+                    uint32_t choice, cost;
+                    best_param_w(S, B, (uint32_t)kS - jstart, P, choice, cost);
+                    sm.choice[s][256 + t] = (uint8_t)choice;
+                    const uint32_t wc = reduce_add(cost);
+                    const uint32_t wf = __ballot_sync(0xffffffffu, choice < 0x80u && choice > 14u);
+                    if (lane == 0) { sm.lvlcost[s][8][warp] = wc; sm.lvlfive[s][8][warp] = wf ? 1 : 0; }
+#pragma unroll
+                    for (int lv = 7; lv >= 3; lv--) {
+                        const int stride = 1 << (7 - lv);
+                        S += __shfl_xor_sync(0xffffffffu, S, stride);
+                        const uint32_t ob = __shfl_xor_sync(0xffffffffu, B, stride);
+                        B = ob > B ? ob : B;
+                        if ((lane & (2 * stride - 1)) == 0)
+                            sc.node[s][(1u << lv) + ((uint32_t)t >> (8 - lv))] = S | ((unsigned long long)B << 48);
+                    }
+                }
+            } else
 #pragma unroll 1
             for (uint32_t it = 0; it < 2; it++) {
                 int32_t A[kXn], B[kXn];
@@ -951,8 +1202,12 @@ __global__ void __launch_bounds__(kT, kCtasPerSm) zf_encode_stereo_v3_kernel(con
                     }
                 }
                 const uint32_t cnt = ((uint32_t)kN >> lvl) - (j == 0 ? d.order : 0u);  // rice.zig:356,371
-                if (__any_sync(0xffffffffu, (S >> 32) != 0)) best_param_nw(S, B, cnt, d.P, choice, cost);
-                else best_param_32((uint32_t)S, B, cnt, d.P, choice, cost);
+                if constexpr (WIDE) {
+                    best_param_w(S, B, cnt, d.P, choice, cost);
+                } else {
+                    if (__any_sync(0xffffffffu, (S >> 32) != 0)) best_param_nw(S, B, cnt, d.P, choice, cost);
+                    else best_param_32((uint32_t)S, B, cnt, d.P, choice, cost);
+                }
                 if (m >= 1) sm.choice[s][m] = (uint8_t)choice;
                 else cost = 0;
                 const bool five = m >= 1 && choice < 0x80u && choice > 14u;  // isRice2, rice.zig:74-76
