@@ -28,6 +28,9 @@ WORKLOADS = {
     "c1_16bit_44k1_60s": (16, 44100, 60),
     "c2_24bit_96k_600s": (24, 96000, 600),
     "c3_32bit_192k_600s": (32, 192000, 600),
+    # BASELINE config 5: the 10-hour stream in eight contiguous frame-range shards; one shard (75 min, 2.6 GB of PCM)
+    # per GPU, so `--gpus 8` under torchrun is the whole stream
+    "c5_24bit_96k_10h_shard8": (24, 96000, 4500),
 }
 DEFAULT_WORKLOAD = "c2_24bit_96k_600s"
 BLOCK = 4096

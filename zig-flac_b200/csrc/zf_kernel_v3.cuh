@@ -77,7 +77,7 @@ struct Smem {
     unsigned long long mbar;
     unsigned long long out_off;
     Dec dec[4];
-    long long warm[4][4];             // first four samples of every candidate (warm-ups, CONSTANT value)
+    typename Arith<BYTES>::T warm[4][4];  // first four samples of every candidate (warm-ups, CONSTANT value)
     uint32_t scan[2][kW];
     uint32_t crc_part[kW], par_part[kW];
     uint32_t next_frame;
@@ -499,11 +499,18 @@ ZF_DEVICE void put_wide(BitW &bw, long long value, uint32_t width) {
     }
 }
 
-ZF_DEVICE void sub_head(BitW &bw, const long long (&warm)[4], int t, const Sub &u) {
+// a sample field: up to 33 bits with 64-bit candidates, at most 25 bits otherwise
+ZF_DEVICE void put_sample(BitW &bw, long long value, uint32_t width) { put_wide(bw, value, width); }
+ZF_DEVICE void put_sample(BitW &bw, int32_t value, uint32_t width) {
+    bw.put((uint32_t)value & (0xffffffffu >> (32u - width)), width);
+}
+
+template <typename TT>
+ZF_DEVICE void sub_head(BitW &bw, const TT (&warm)[4], int t, const Sub &u) {
     if (u.kind == kConstant) {  // :269-279: 0x00, then the un-shifted sample at full depth
         if (t == 0) {
             bw.put(0, 8);
-            put_wide(bw, warm[0], u.depth_ch);
+            put_sample(bw, warm[0], u.depth_ch);
         }
         return;
     }
@@ -519,7 +526,7 @@ ZF_DEVICE void sub_head(BitW &bw, const long long (&warm)[4], int t, const Sub &
         bw.put(((8u | u.order) << 1) | (u.waste ? 1u : 0u), 8);
         if (u.waste) bw.put(1u, u.waste);
 #pragma unroll 1
-        for (uint32_t k = 0; k < u.order; k++) put_wide(bw, warm[k] >> u.waste, u.bps);
+        for (uint32_t k = 0; k < u.order; k++) put_sample(bw, (TT)(warm[k] >> u.waste), u.bps);
         bw.put((u.method << 4) | u.po, 6);
     }
     if (u.at_start) {  // :341-357
@@ -534,6 +541,7 @@ ZF_DEVICE void sub_head(BitW &bw, const long long (&warm)[4], int t, const Sub &
 
 // this thread's residuals / samples, any kind (the common FIXED non-escape case of both subframes at once is
 // handled by the caller)
+template <bool WIDE>
 ZF_DEVICE void sub_body(BitW &bw, int t, const Sub &u, const uint32_t (&v)[kS]) {
     if (u.kind == kConstant) return;
     // rare paths: compact code (a 4-trip loop; v[] must stay in registers, so select instead of indexing)
@@ -541,7 +549,7 @@ ZF_DEVICE void sub_body(BitW &bw, int t, const Sub &u, const uint32_t (&v)[kS]) 
     const uint32_t jstart = (t == 0 && !verb) ? u.order : 0u;
     const uint32_t wd = verb ? u.bps : (u.choice & 0x7fu);  // raw field width of VERBATIM samples / escaped residuals
     if ((verb || esc) && wd == 0) return;
-    const uint32_t rawmask = wd >= 32u ? 0xffffffffu : (0xffffffffu >> (32u - (wd ? wd : 1u)));
+    const uint32_t rawmask = (WIDE && wd >= 32u) ? 0xffffffffu : (0xffffffffu >> (32u - (wd ? wd : 1u)));
     const uint32_t k = u.choice & 31u, one = 1u << k, m = one - 1u, len = k + 1u;
 #pragma unroll 1
     for (int j0 = 0; j0 < kS; j0 += 4) {
@@ -553,7 +561,7 @@ ZF_DEVICE void sub_body(BitW &bw, int t, const Sub &u, const uint32_t (&v)[kS]) 
             z = j0 == 12 ? v[12 + jj] : z;
             if ((uint32_t)(j0 + jj) >= jstart) {
                 if (verb) {                                                               // :282-301
-                    if (wd > 32u) {  // 33-bit samples of the 32-bit side channel
+                    if (WIDE && wd > 32u) {  // 33-bit samples of the 32-bit side channel
                         bw.put((u.vhi >> (j0 + jj)) & 1u, 1);
                         bw.put(z, 32);
                     } else {
@@ -1034,7 +1042,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             const uint32_t depth_ch = depth + (s == 3 ? 1u : 0u);
             Dec d;
             d.pad[0] = d.pad[1] = 0;
-            d.waste = (orv == 0) ? depth_ch : ctz64(orv);
+            d.waste = (orv == 0) ? depth_ch : (WIDE ? ctz64(orv) : ctz32((uint32_t)orv));
             d.bps = depth_ch - d.waste;
             d.order = 0;
             const uint32_t lim = d.bps > 16 ? 30u : 14u;
@@ -1346,7 +1354,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #pragma unroll
                     for (int j = 0; j < kS; j++) v[j] = ch ? vb[j] : va[j];
                     BitW w = ch ? wb : wa;
-                    sub_body(w, t, ch ? ub : ua, v);
+                    sub_body<WIDE>(w, t, ch ? ub : ua, v);
                     if (ch) wb = w;
                     else wa = w;
                 }
