@@ -1250,29 +1250,42 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         Sub ua, ub;
         uint32_t ch_type = 1, sa = 0, sb = 1;
         {
+            // lane 8 s + i looks at partition order i + 1 of candidate s (its 16 partial sums), lane 8 s also at order 0;
+            // key = (bits << 5) | (15 - order) << 1 | method: the minimum is the smallest size, then the highest order
+            uint32_t key = 0xffffffffu;
+            {
+                const uint32_t s = (uint32_t)lane >> 3, l = ((uint32_t)lane & 7u) + 1u;
+                if (sm.dec[s].kind == kFixed) {
+                    const uint4 *cp = reinterpret_cast<const uint4 *>(&sm.lvlcost[s][l][0]);
+                    const uint4 c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3];
+                    const uint4 fv = *reinterpret_cast<const uint4 *>(&sm.lvlfive[s][l][0]);
+                    const uint32_t cost = (c0.x + c0.y + c0.z + c0.w) + (c1.x + c1.y + c1.z + c1.w) +
+                                          (c2.x + c2.y + c2.z + c2.w) + (c3.x + c3.y + c3.z + c3.w);
+                    const uint32_t method = (fv.x | fv.y | fv.z | fv.w) ? 1u : 0u;
+                    const uint32_t bc = cost + ((4u + method) << l);  // :394
+                    key = (bc << 5) | ((15u - l) << 1) | method;
+                    if (l == 1u) {
+                        const uint32_t m0 = sm.lvlfive[s][0][0] ? 1u : 0u;
+                        const uint32_t k0 = ((sm.lvlcost[s][0][0] + 4u + m0) << 5) | (15u << 1) | m0;
+                        key = k0 < key ? k0 : key;
+                    }
+                }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other < key ? other : key;
+                }
+            }
             uint32_t kind[4], est[4], pom[4];
 #pragma unroll
             for (int s = 0; s < 4; s++) {
                 kind[s] = sm.dec[s].kind;
                 est[s] = sm.dec[s].est;
                 pom[s] = 0;
+                const uint32_t bk = __shfl_sync(0xffffffffu, key, 8 * s);
                 if (kind[s] == kFixed) {
-                    uint32_t key = 0xffffffffu, method = 0;
-                    if (lane <= 8) {
-                        const uint4 *cp = reinterpret_cast<const uint4 *>(&sm.lvlcost[s][lane][0]);
-                        const uint4 c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3];
-                        const uint4 fv = *reinterpret_cast<const uint4 *>(&sm.lvlfive[s][lane][0]);
-                        const uint32_t cost = (c0.x + c0.y + c0.z + c0.w) + (c1.x + c1.y + c1.z + c1.w) +
-                                              (c2.x + c2.y + c2.z + c2.w) + (c3.x + c3.y + c3.z + c3.w);
-                        method = (fv.x | fv.y | fv.z | fv.w) ? 1u : 0u;
-                        const uint32_t bc = cost + ((4u + method) << lane);  // :394
-                        key = (bc << 4) | (15u - (uint32_t)lane);            // minimum cost, then the highest level
-                    }
-                    const uint32_t bk = reduce_min(key);
-                    const uint32_t bpo = 15u - (bk & 15u);
-                    const uint32_t bmethod = __shfl_sync(0xffffffffu, method, (int)bpo);
-                    const uint32_t best = bk >> 4;
-                    if (best < est[s]) { est[s] = best; pom[s] = bpo | (bmethod << 4); }
+                    const uint32_t best = bk >> 5;
+                    if (best < est[s]) { est[s] = best; pom[s] = (15u - ((bk >> 1) & 15u)) | ((bk & 1u) << 4); }
                     else kind[s] = kVerbatim;
                 }
             }
