@@ -188,3 +188,58 @@ def test_pageable_and_pinned_host_buffers_agree(zf, oracle):
             got, sizes = enc.encode_pcm(pcm, n)
         assert np.array_equal(sizes, ref_sizes), per
         assert got.tobytes() == ref.tobytes(), per
+
+
+def test_full_size_config2_properties(zf, oracle):
+    """BASELINE config 2 at full size (24-bit / 96 kHz / 600 s: 14 063 frames, 345.6 MB of PCM), checked through
+    size-independent properties: the frame sizes add up to the stream, two frame-range shards concatenate to the
+    single-shot stream (what the multi-GPU driver relies on), the independent decoder accepts every frame (CRC-8 and
+    CRC-16 valid) and returns the PCM (lossless), and a slice of the stream is byte-identical to the oracle's."""
+    bits, rate, seconds = 24, 96000, 600
+    n = rate * seconds
+    pcm = zf.synth_pcm(n, rate, bits)
+    with zf.Encoder(zf.Config.default(2, bits), rate, max_frames_per_batch=2048) as enc:
+        got, sizes = enc.encode_pcm(pcm, n)
+        assert sizes.size == (n + 4095) // 4096 and int(sizes.astype(np.int64).sum()) == got.size
+        half = (sizes.size // 2) * 4096
+        a, sa = enc.encode_pcm(pcm[: half * 6], half, 0)
+        b, sb = enc.encode_pcm(pcm[half * 6:], n - half, sizes.size // 2)
+    assert np.array_equal(np.concatenate([sa, sb]), sizes)
+    assert np.concatenate([a, b]).tobytes() == got.tobytes()
+    # oracle on the first and the last 100 frames
+    k = 100 * 4096
+    ref, rs = oracle.encode_pcm(pcm[: k * 6], k, oracle.config(2, bits), rate, 0, threads=8)
+    assert ref.tobytes() == got[: ref.size].tobytes()
+    f0 = sizes.size - 100
+    ref, rs = oracle.encode_pcm(pcm[f0 * 4096 * 6:], n - f0 * 4096, oracle.config(2, bits), rate, f0, threads=8)
+    assert ref.tobytes() == got[got.size - ref.size:].tobytes()
+    # independent decoder: every frame's CRCs, lossless samples
+    d = oracle.decode(oracle.wrap_frames(got, 2, bits, rate, total_samples=n), max_frames=1 << 14)
+    assert d["rc"] == 0 and d["n_frames"] == sizes.size
+    raw = np.frombuffer(pcm, dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+    expect = (raw[:, 0] | (raw[:, 1] << 8) | (raw[:, 2] << 16))
+    expect = (expect ^ 0x800000) - 0x800000
+    assert np.array_equal(d["pcm"], expect)
+
+
+def test_error_behaviour(zf, oracle):
+    """Writer.Error.WriteFailed <-> ZF_ERR_OUT_TOO_SMALL, argument checks, and the handle stays usable afterwards."""
+    bits, rate = 16, 44100
+    n = 4096 * 6 + 10
+    pcm = zf.synth_pcm(n, rate, bits)
+    ref, ref_sizes = oracle.encode_pcm(pcm, n, oracle.config(2, bits), rate)
+    with zf.Encoder(zf.Config.default(2, bits), rate, max_frames_per_batch=4) as enc:
+        small = np.empty(1000, dtype=np.uint8)
+        with pytest.raises(zf.FlacGpuError) as ei:
+            enc.encode_pcm(pcm, n, out=small)
+        assert ei.value.status == zf.ZF_ERR_OUT_TOO_SMALL
+        got, sizes = enc.encode_pcm(pcm, n)  # the same handle still works
+        assert np.array_equal(sizes, ref_sizes) and got.tobytes() == ref.tobytes()
+        empty, es = enc.encode_pcm(pcm[:0], 0)
+        assert empty.size == 0 and es.size == 0
+    for bad in (dict(bit_depth=20), dict(block_size=8192), dict(max_rice_order=9), dict(max_rice_param=31)):
+        kw = dict(bit_depth=16)
+        kw.update(bad)
+        depth = kw.pop("bit_depth")
+        with pytest.raises(zf.FlacGpuError):
+            zf.Encoder(zf.Config(2, depth, **kw), rate)
