@@ -31,6 +31,8 @@ WORKLOADS = {
     # BASELINE config 5: the 10-hour stream in eight contiguous frame-range shards; one shard (75 min, 2.6 GB of PCM)
     # per GPU, so `--gpus 8` under torchrun is the whole stream
     "c5_24bit_96k_10h_shard8": (24, 96000, 4500),
+    # not a BASELINE config: config 1's format at bandwidth-config length (development aid)
+    "x1_16bit_44k1_3600s": (16, 44100, 3600),
 }
 DEFAULT_WORKLOAD = "c2_24bit_96k_600s"
 BLOCK = 4096

@@ -43,7 +43,10 @@ constexpr int kW = kT / 32;
 constexpr int kPadWords = 8;     // 32 zero bytes in front of the PCM: history of thread 0
 constexpr int kCrcChunkWords = 16;
 // resident CTAs per SM: 16/24-bit: 80 registers, ~66 KB of shared memory each; 32-bit (64-bit chains): 128 registers, ~87 KB
-template <int BYTES> struct CtasPerSm { static constexpr int value = BYTES == 4 ? 2 : 3; };
+#ifndef ZF_V3_CTAS16
+#define ZF_V3_CTAS16 3
+#endif
+template <int BYTES> struct CtasPerSm { static constexpr int value = BYTES == 4 ? 2 : BYTES == 2 ? ZF_V3_CTAS16 : 3; };
 
 // candidate-channel arithmetic: 32-bit PCM needs 33 bits for the side channel and 37 for its fourth difference
 template <int BYTES> struct Arith { typedef int32_t T; typedef uint32_t U; };
@@ -1350,15 +1353,19 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 const uint32_t ka = ua.choice, onea = 1u << ka, ma = onea - 1u;
                 const uint32_t kb = ub.choice, oneb = 1u << kb, mb = oneb - 1u;
                 const uint32_t ja = (t == 0) ? ua.order : 0u, jb = (t == 0) ? ub.order : 0u;
+                // :363-372: q zeros, a one, k remainder bits.  Four trips over one piece of code (the arrays rotate by
+                // four registers per trip): code size counts as much as instruction count here
+#pragma unroll 1
+                for (int j0 = 0; j0 < kS; j0 += 4) {
 #pragma unroll
-                for (int j = 0; j < kS; j++) {  // :363-372: q zeros, a one, k remainder bits
-                    if (j < 4) {
-                        if ((uint32_t)j >= ja) wa.put(onea | (va[j] & ma), (va[j] >> ka) + lena);
-                        if ((uint32_t)j >= jb) wb.put(oneb | (vb[j] & mb), (vb[j] >> kb) + lenb);
-                    } else {
-                        wa.put(onea | (va[j] & ma), (va[j] >> ka) + lena);
-                        wb.put(oneb | (vb[j] & mb), (vb[j] >> kb) + lenb);
+                    for (int jj = 0; jj < 4; jj++) {
+                        // the warm-up samples of thread 0 are not coded: an empty field is a no-op
+                        const bool oa = (uint32_t)(j0 + jj) >= ja, ob = (uint32_t)(j0 + jj) >= jb;
+                        wa.put(oa ? (onea | (va[jj] & ma)) : 0u, oa ? ((va[jj] >> ka) + lena) : 0u);
+                        wb.put(ob ? (oneb | (vb[jj] & mb)) : 0u, ob ? ((vb[jj] >> kb) + lenb) : 0u);
                     }
+#pragma unroll
+                    for (int jj = 0; jj < kS - 4; jj++) { va[jj] = va[jj + 4]; vb[jj] = vb[jj + 4]; }
                 }
             } else {
 #pragma unroll 1
