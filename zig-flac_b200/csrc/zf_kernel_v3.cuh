@@ -272,14 +272,14 @@ struct ChainW {
 };
 
 // `order` passes of in-place differencing: afterwards x[i] is the order-th difference for i >= order
+// (one rolled pass per order: the low positions a pass would not need are differenced too -- nobody reads them -- so
+// that every pass is the same piece of code)
 template <typename TT>
 ZF_DEVICE void diff_in_place(TT (&x)[kXn], uint32_t order) {
+#pragma unroll 1
+    for (uint32_t k = 0; k < order; k++) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if ((uint32_t)k < order) {
-#pragma unroll
-            for (int i = kXn - 1; i > k; i--) x[i] -= x[i - 1];
-        }
+        for (int i = kXn - 1; i > 0; i--) x[i] -= x[i - 1];
     }
 }
 
@@ -1406,7 +1406,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                     uint32_t a = 0;
                     if (end >= (uint32_t)kCrcChunkWords) {
                         const uint4 *p = reinterpret_cast<const uint4 *>(sm.bits + (end - (uint32_t)kCrcChunkWords));
-#pragma unroll
+#pragma unroll 1
                         for (int k = 0; k < kCrcChunkWords / 4; k++) {
                             const uint4 v = p[k];
                             a = q_fold((a << 4) ^ (a << 2) ^ v.x);
