@@ -403,6 +403,7 @@ struct BitW {
     // q zero bits, then the len-bit field val (len 1..31)
     ZF_DEVICE void put_code(uint32_t q, uint32_t val, uint32_t len) {
         if (q + len > 32u) {  // long unary run (rare)
+#pragma unroll 1
             while (q >= 32u) { put(0, 32); q -= 32u; }
             put(0, q);
             q = 0;
@@ -723,6 +724,7 @@ ZF_NOINLINE void copy_out(const Smem<BYTES> &sm, uint8_t *out, unsigned long lon
     const uint32_t nq = (fbytes - h) >> 4;
     uint4 *dq = reinterpret_cast<uint4 *>(dst + h);
     const uint32_t o = lead + h, w0 = o >> 2, sh = 8u * (o & 3u);
+#pragma unroll 1
     for (uint32_t k = t; k < nq; k += kT) {
         const uint32_t *p = sm.bits + w0 + 4u * k;
         const uint32_t b0 = p[0], b1 = p[1], b2 = p[2], b3 = p[3], b4 = p[4];
@@ -757,6 +759,7 @@ ZF_DEVICE void zero_bits(Smem<BYTES> &sm, int t, const Pend &P) {
     const uint4 z = {0, 0, 0, 0};
     const uint32_t nwords = (P.lead + P.fbytes) >> 2;
     const uint32_t n4 = P.fits ? ((nwords + 2u + 3u) >> 2) : (uint32_t)(BitBufWords<BYTES>::value + 8) / 4u;
+#pragma unroll 1
     for (uint32_t k = t; k < n4; k += kT) bz[k] = z;
 }
 
@@ -1082,39 +1085,19 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 
         // ================= pass 2: leaf statistics of the chosen order, level-8 search, tree levels 7..3 ==========
         {
-#define ZF3_LEAF(SLOT, X)                                                                           \
+// leaf statistics of one candidate: residual of the chosen order in place, then abs-sum, minimum and maximum of the
+// thread's sixteen residuals (partition 0 skips the warm-ups, rice.zig:308)
+#define ZF3_LEAF(SLOT, X, SUM, MN, MX)                                                              \
     {                                                                                               \
-        const uint32_t order = sm.dec[SLOT].order, waste = sm.dec[SLOT].waste, P = sm.dec[SLOT].P;  \
+        const uint32_t order = sm.dec[SLOT].order;                                                  \
         diff_in_place(X, order);                                                                    \
         const uint32_t jstart = (t == 0) ? order : 0u;                                              \
-        int32_t mn = 0, mx = 0;                                                                     \
-        uint32_t sum = 0;                                                                           \
         _Pragma("unroll") for (int j = 0; j < kS; j++) {                                            \
             int32_t r = X[kH + j];                                                                  \
-            if (j < 4) r = ((uint32_t)j >= jstart) ? r : 0; /* partition 0 skips the warm-ups, rice.zig:308 */ \
-            sum += uabs(r);                                                                         \
-            mn = r < mn ? r : mn;                                                                   \
-            mx = r > mx ? r : mx;                                                                   \
-        }                                                                                           \
-        mn >>= waste;                                                                               \
-        mx >>= waste;                                                                               \
-        const uint32_t zm = zigzag(mn), zx = zigzag(mx);                                            \
-        uint32_t B = bitlen32(zm > zx ? zm : zx);  /* bit length of the OR of the zigzags */        \
-        const uint32_t S32 = sum >> waste;         /* rice.calcSums, rice.zig:288-340 */            \
-        uint32_t choice, cost;                                                                      \
-        best_param_32(S32, B, (uint32_t)kS - jstart, P, choice, cost);                              \
-        sm.choice[SLOT][256 + t] = (uint8_t)choice;                                                 \
-        const uint32_t wc = reduce_add(cost);                                                       \
-        const uint32_t wf = __ballot_sync(0xffffffffu, choice < 0x80u && choice > 14u);             \
-        if (lane == 0) { sm.lvlcost[SLOT][8][warp] = wc; sm.lvlfive[SLOT][8][warp] = wf ? 1 : 0; }  \
-        unsigned long long S = S32;                                                                 \
-        _Pragma("unroll") for (int lv = 7; lv >= 3; lv--) {                                         \
-            const int stride = 1 << (7 - lv);                                                       \
-            S += __shfl_xor_sync(0xffffffffu, S, stride);                                           \
-            const uint32_t ob = __shfl_xor_sync(0xffffffffu, B, stride);                            \
-            B = ob > B ? ob : B;                                                                    \
-            if ((lane & (2 * stride - 1)) == 0)                                                     \
-                sc.node[SLOT][(1u << lv) + ((uint32_t)t >> (8 - lv))] = S | ((unsigned long long)B << 48); \
+            if (j < 4) r = ((uint32_t)j >= jstart) ? r : 0;                                         \
+            SUM += uabs(r);                                                                         \
+            MN = r < MN ? r : MN;                                                                   \
+            MX = r > MX ? r : MX;                                                                   \
         }                                                                                           \
     }
             if constexpr (WIDE) {
@@ -1169,8 +1152,38 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                     }
                 }
                 const uint32_t slot_a = it ? 0u : 3u, slot_b = it ? 1u : 2u;
-                if (sm.dec[slot_a].kind == kFixed) ZF3_LEAF(slot_a, A)
-                if (sm.dec[slot_b].kind == kFixed) ZF3_LEAF(slot_b, B)
+                const bool fix_a = sm.dec[slot_a].kind == kFixed, fix_b = sm.dec[slot_b].kind == kFixed;
+                uint32_t sum_a = 0, sum_b = 0;
+                int32_t mn_a = 0, mx_a = 0, mn_b = 0, mx_b = 0;
+                if (fix_a) ZF3_LEAF(slot_a, A, sum_a, mn_a, mx_a)
+                if (fix_b) ZF3_LEAF(slot_b, B, sum_b, mn_b, mx_b)
+#pragma unroll 1
+                for (uint32_t h = 0; h < 2; h++) {  // one copy of: width, leaf parameter, tree levels 7..3
+                    if (!(h ? fix_b : fix_a)) continue;
+                    const uint32_t slot = h ? slot_b : slot_a;
+                    const uint32_t order = sm.dec[slot].order, waste = sm.dec[slot].waste, P = sm.dec[slot].P;
+                    const uint32_t jstart = (t == 0) ? order : 0u;
+                    const int32_t mn = (h ? mn_b : mn_a) >> waste, mx = (h ? mx_b : mx_a) >> waste;
+                    const uint32_t zm = zigzag(mn), zx = zigzag(mx);
+                    uint32_t B = bitlen32(zm > zx ? zm : zx);        // bit length of the OR of the zigzags
+                    const uint32_t S32 = (h ? sum_b : sum_a) >> waste;  // rice.calcSums, rice.zig:288-340
+                    uint32_t choice, cost;
+                    best_param_32(S32, B, (uint32_t)kS - jstart, P, choice, cost);
+                    sm.choice[slot][256 + t] = (uint8_t)choice;
+                    const uint32_t wc = reduce_add(cost);
+                    const uint32_t wf = __ballot_sync(0xffffffffu, choice < 0x80u && choice > 14u);
+                    if (lane == 0) { sm.lvlcost[slot][8][warp] = wc; sm.lvlfive[slot][8][warp] = wf ? 1 : 0; }
+                    unsigned long long S = S32;
+#pragma unroll
+                    for (int lv = 7; lv >= 3; lv--) {
+                        const int stride = 1 << (7 - lv);
+                        S += __shfl_xor_sync(0xffffffffu, S, stride);
+                        const uint32_t ob = __shfl_xor_sync(0xffffffffu, B, stride);
+                        B = ob > B ? ob : B;
+                        if ((lane & (2 * stride - 1)) == 0)
+                            sc.node[slot][(1u << lv) + ((uint32_t)t >> (8 - lv))] = S | ((unsigned long long)B << 48);
+                    }
+                }
             }
 #undef ZF3_LEAF
         }
