@@ -431,7 +431,7 @@ ZF_DEVICE uint32_t q_fold(uint32_t v) {
 }
 ZF_DEVICE uint32_t q_mulmod(uint32_t a, uint32_t b) {  // a, b < 2^15
     uint32_t acc = 0;
-#pragma unroll
+#pragma unroll 3
     for (int i = 0; i < 15; i++) acc ^= ((b >> i) & 1u) ? (a << i) : 0u;
     return q_fold(acc);  // 29-bit product: one round suffices
 }
@@ -788,8 +788,8 @@ ZF_DEVICE uint32_t header_byte(const uint8_t *crc8tab, int lane, unsigned long l
     // CRC-8 (poly 0x07, init 0) is linear: byte k contributes T^(len-1-k)[byte], T = one table step
     uint32_t v = (k < len - 1u) ? b : 0u;
     const uint32_t steps = len - 1u - (k < len - 1u ? k : len - 1u);
-    for (uint32_t r = 0; r < 10u; r++)
-        if (r < steps) v = crc8tab[v];
+#pragma unroll 1
+    for (uint32_t r = 0; r < steps; r++) v = crc8tab[v];
     const uint32_t crc = reduce_xor(v);
     if (k == len - 1u) b = crc;
     return b;
@@ -1328,7 +1328,10 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         const uint32_t len_b = sub_count<BYTES>(sm, t, sb, ub, vb);
         uint32_t ex_a, ex_b, tot_a, tot_b;
         block_scan2(sm.scan, t, len_a, len_b, ex_a, ex_b, tot_a, tot_b);
-        const uint32_t hdr_bits = 8u * header_len(frame_number, (uint32_t)kN, job.sample_rate);
+        // 4 fixed bytes + the UTF-8-like frame number + CRC-8 (block size 4096 and table sample rates have no trailer)
+        const uint32_t fn32 = (uint32_t)frame_number;
+        const uint32_t hdr_bits = 8u * (6u + (fn32 >= 0x80u) + (fn32 >= 0x800u) + (fn32 >= 0x10000u) + (fn32 >= 0x200000u) +
+                                        (fn32 >= 0x4000000u));
         const uint32_t total_bits = hdr_bits + tot_a + tot_b;
         const uint32_t fbytes = (total_bits + 7u) >> 3;
         const uint32_t size = fbytes + 2u;
