@@ -456,10 +456,10 @@ ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u
     u.at_start = false;
 #pragma unroll
     for (int j = 0; j < kS; j++) v[j] = 0;
-    if (u.kind == kConstant) return t == 0 ? 8u + u.depth_ch : 0u;
+    if (__builtin_expect(u.kind == kConstant, 0)) return t == 0 ? 8u + u.depth_ch : 0u;
     typename Arith<BYTES>::T x[kXn];
     load_x<BYTES>(sm.raw, t, slot, x);
-    if (u.kind == kVerbatim) {
+    if (__builtin_expect(u.kind == kVerbatim, 0)) {
 #pragma unroll
         for (int j = 0; j < kS; j++) {
             const typename Arith<BYTES>::T sv = x[kH + j] >> u.waste;
@@ -479,7 +479,7 @@ ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u
     uint32_t bits = (t == 0) ? 8u + u.waste + u.order * u.bps + 6u : 0u;
     const bool esc = (u.choice & 0x80u) != 0;
     if (u.at_start) bits += 4u + u.method + (esc ? 5u : 0u);
-    if (esc) return bits + (u.choice & 0x7fu) * cnt;
+    if (__builtin_expect(esc, 0)) return bits + (u.choice & 0x7fu) * cnt;
     uint32_t qs = 0, mq = 0;
 #pragma unroll
     for (int j = 0; j < kS; j++) {
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
     while (f < job.n_frames) {
         const uint32_t fidx = job.frame_base + f;
         const unsigned long long frame_number = job.first_frame_number + fidx;
-        if (tma) {
+        if (__builtin_expect(tma, 1)) {
             mbar_wait(&sm.mbar, phase);
             phase ^= 1u;
         } else {
@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 if constexpr (WIDE) {
                     best_param_w(S, B, cnt, d.P, choice, cost);
                 } else {
-                    if (__any_sync(0xffffffffu, (S >> 32) != 0)) best_param_nw(S, B, cnt, d.P, choice, cost);
+                    if (__builtin_expect(__any_sync(0xffffffffu, (S >> 32) != 0), 0)) best_param_nw(S, B, cnt, d.P, choice, cost);
                     else best_param_32((uint32_t)S, B, cnt, d.P, choice, cost);
                 }
                 if (m >= 1) sm.choice[s][m] = (uint8_t)choice;
@@ -1365,7 +1365,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             const uint32_t lena = ua.choice + 1u, lenb = ub.choice + 1u;
             const bool fast = ua.kind == kFixed && ub.kind == kFixed && !((ua.choice | ub.choice) & 0x80u) &&
                               ua.maxq + lena <= 32u && ub.maxq + lenb <= 32u;
-            if (fast) {  // every codeword is one field of at most 32 bits: two independent chains, no branches
+            if (__builtin_expect(fast, 1)) {  // every codeword is one field of at most 32 bits: two independent chains, no branches
                 const uint32_t ka = ua.choice, onea = 1u << ka, ma = onea - 1u;
                 const uint32_t kb = ub.choice, oneb = 1u << kb, mb = oneb - 1u;
                 const uint32_t ja = (t == 0) ? ua.order : 0u, jb = (t == 0) ? ub.order : 0u;
