@@ -49,8 +49,6 @@ struct Slot {  // one in-flight batch: device buffers + pinned staging
     unsigned long long *d_total = nullptr;
     unsigned long long *h_total = nullptr;  // pinned: [0] total, [1] status
     cudaStream_t stream = nullptr;
-    cudaStream_t aux = nullptr;              // the short last frame is encoded here, concurrently
-    cudaEvent_t ev_in = nullptr, ev_tail = nullptr;
     uint8_t *d_tail = nullptr;               // private output of the last-frame launch
     unsigned long long *d_tail_meta = nullptr;  // [0] desc, [1] total, [2] lo32: frame size
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
@@ -158,22 +156,39 @@ int setup_kernels(zf_encoder *e) {
     return ZF_OK;
 }
 
-template <int BYTES>
-void launch_stereo(bool full, int grid, size_t smem, cudaStream_t s, const zf::FrameJob &job) {
-    if (full) zf::zf_encode_stereo_full_kernel<BYTES><<<grid, zf::kThreads, smem, s>>>(job);
-    else zf::zf_encode_stereo_kernel<BYTES, false><<<grid, zf::kThreads, smem, s>>>(job);
+// `overlap`: programmatic dependent launch -- the kernel may start as soon as the kernel in front of it in the stream
+// has released its dependents (the one-CTA last-frame launch does so at once), instead of after its end
+template <typename K>
+void launch_k(K kernel, int grid, int block, size_t smem, cudaStream_t s, bool overlap, const zf::FrameJob &job) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = overlap ? 1u : 0u;
+    cudaLaunchKernelEx(&cfg, kernel, job);
 }
 
-void launch_one(zf_encoder *e, bool full, int grid, cudaStream_t s, const zf::FrameJob &job) {
+template <int BYTES>
+void launch_stereo(bool full, int grid, size_t smem, cudaStream_t s, bool overlap, const zf::FrameJob &job) {
+    if (full) launch_k(zf::zf_encode_stereo_full_kernel<BYTES>, grid, zf::kThreads, smem, s, overlap, job);
+    else launch_k(zf::zf_encode_stereo_kernel<BYTES, false>, grid, zf::kThreads, smem, s, overlap, job);
+}
+
+void launch_one(zf_encoder *e, bool full, int grid, cudaStream_t s, const zf::FrameJob &job, bool overlap = false) {
     const int bytes = e->cfg.bit_depth / 8;
     if (e->stereo) {
-        if (bytes == 2) launch_stereo<2>(full, grid, e->smem_stereo, s, job);
-        else if (bytes == 3) launch_stereo<3>(full, grid, e->smem_stereo, s, job);
-        else launch_stereo<4>(full, grid, e->smem_stereo, s, job);
+        if (bytes == 2) launch_stereo<2>(full, grid, e->smem_stereo, s, overlap, job);
+        else if (bytes == 3) launch_stereo<3>(full, grid, e->smem_stereo, s, overlap, job);
+        else launch_stereo<4>(full, grid, e->smem_stereo, s, overlap, job);
     } else {
-        if (bytes == 2) zf::zf_encode_indep_kernel<2><<<grid, zf::kThreads, e->smem_indep, s>>>(job);
-        else if (bytes == 3) zf::zf_encode_indep_kernel<3><<<grid, zf::kThreads, e->smem_indep, s>>>(job);
-        else zf::zf_encode_indep_kernel<4><<<grid, zf::kThreads, e->smem_indep, s>>>(job);
+        if (bytes == 2) launch_k(zf::zf_encode_indep_kernel<2>, grid, zf::kThreads, e->smem_indep, s, overlap, job);
+        else if (bytes == 3) launch_k(zf::zf_encode_indep_kernel<3>, grid, zf::kThreads, e->smem_indep, s, overlap, job);
+        else launch_k(zf::zf_encode_indep_kernel<4>, grid, zf::kThreads, e->smem_indep, s, overlap, job);
     }
 }
 
@@ -214,11 +229,14 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.max_rice_order == 8;
     // the 1-D TMA bulk copy needs 16-byte aligned sources; frame strides are multiples of 16 already
     job.use_tma = ((uintptr_t)d_pcm & 15u) == 0 ? 1u : 0u;
-    const bool split_tail = tail && full;  // overlap the one-CTA last-frame launch with the full-frame kernel
+    // The short last frame is a one-CTA launch of the general kernel IN FRONT of the persistent full-frame kernel, which is
+    // launched as its programmatic dependent: the short-frame CTA releases its dependents at once, so both run together
+    // (launched after, or on another stream, it would only get an SM when the persistent kernel ends).
+    const bool split_tail = tail && full;
+    const uint32_t ring = sl.kev_count % kRing;
+    if (full) ZF_CUDA(cudaEventRecord(sl.kev[2 * ring], s));
     if (split_tail) {
         ZF_CUDA(cudaMemsetAsync(sl.d_tail_meta, 0, sizeof(unsigned long long) * 4, s));
-        ZF_CUDA(cudaEventRecord(sl.ev_in, s));
-        ZF_CUDA(cudaStreamWaitEvent(sl.aux, sl.ev_in, 0));
         zf::FrameJob tj = job;
         tj.pcm = d_pcm + full * e->frame_pcm_bytes;
         tj.out = sl.d_tail;
@@ -232,8 +250,8 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         tj.first_frame_number = first_frame_number + full;
         tj.block_size = tail;
         tj.ticket = sl.d_ctl + 1;
-        launch_one(e, false, 1, sl.aux, tj);
-        ZF_CUDA(cudaEventRecord(sl.ev_tail, sl.aux));
+        tj.pdl_trigger = 1;
+        launch_one(e, false, 1, s, tj);
         (*launches)++;
     }
     if (full) {
@@ -248,21 +266,18 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
                         table_rate(e->cfg.sample_rate);
         const int occ = v3 ? e->occ_v3 : fast ? e->occ_full : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
-        const uint32_t ring = sl.kev_count % kRing;
-        ZF_CUDA(cudaEventRecord(sl.kev[2 * ring], s));
         if (v3) {
-            if (e->cfg.bit_depth == 16) zf::v3::zf_encode_stereo_v3_kernel<2><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
-            else if (e->cfg.bit_depth == 24) zf::v3::zf_encode_stereo_v3_kernel<3><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
-            else zf::v3::zf_encode_stereo_v3_kernel<4><<<grid, zf::v3::kT, e->smem_v3, s>>>(job);
+            if (e->cfg.bit_depth == 16) launch_k(zf::v3::zf_encode_stereo_v3_kernel<2>, grid, zf::v3::kT, e->smem_v3, s, split_tail, job);
+            else if (e->cfg.bit_depth == 24) launch_k(zf::v3::zf_encode_stereo_v3_kernel<3>, grid, zf::v3::kT, e->smem_v3, s, split_tail, job);
+            else launch_k(zf::v3::zf_encode_stereo_v3_kernel<4>, grid, zf::v3::kT, e->smem_v3, s, split_tail, job);
         } else {
-            launch_one(e, fast, grid, s, job);
+            launch_one(e, fast, grid, s, job, split_tail);
         }
         ZF_CUDA(cudaEventRecord(sl.kev[2 * ring + 1], s));
         sl.kev_count++;
         (*launches)++;
     }
     if (split_tail) {
-        ZF_CUDA(cudaStreamWaitEvent(s, sl.ev_tail, 0));
         zf::zf_append_tail_kernel<<<1, 256, 0, s>>>(sl.d_tail, reinterpret_cast<const uint32_t *>(sl.d_tail_meta + 2), d_out,
                                                     out_cap, d_total, d_sizes, (uint32_t)full, sl.d_ctl + 2);
         (*launches)++;
@@ -295,9 +310,6 @@ int ensure_io(zf_encoder *e, Slot &sl) {
 int slot_init(zf_encoder *e, Slot &sl) {
     const size_t frames = e->cfg.max_frames_per_batch;
     ZF_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-    ZF_CUDA(cudaStreamCreateWithFlags(&sl.aux, cudaStreamNonBlocking));
-    ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
-    ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_tail, cudaEventDisableTiming));
     ZF_CUDA(cudaMalloc(&sl.d_tail, e->max_frame_bytes + 64));
     ZF_CUDA(cudaMalloc(&sl.d_tail_meta, sizeof(unsigned long long) * 4));
     ZF_CUDA(cudaEventCreate(&sl.ev_start));
@@ -315,11 +327,7 @@ int slot_init(zf_encoder *e, Slot &sl) {
 
 void slot_free(Slot &sl) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    if (sl.aux) cudaStreamSynchronize(sl.aux);
     cudaFree(sl.d_tail); cudaFree(sl.d_tail_meta);
-    if (sl.ev_in) cudaEventDestroy(sl.ev_in);
-    if (sl.ev_tail) cudaEventDestroy(sl.ev_tail);
-    if (sl.aux) cudaStreamDestroy(sl.aux);
     cudaFree(sl.d_pcm); cudaFree(sl.d_out); cudaFree(sl.d_sizes); cudaFree(sl.d_desc); cudaFree(sl.d_ctl); cudaFree(sl.d_total);
     cudaFreeHost(sl.h_pcm); cudaFreeHost(sl.h_out); cudaFreeHost(sl.h_sizes); cudaFreeHost(sl.h_total);
     if (sl.ev_start) cudaEventDestroy(sl.ev_start);

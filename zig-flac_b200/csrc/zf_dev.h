@@ -61,6 +61,9 @@ ZF_DEVICE void cp_async16_cg(void *smem_dst, const void *gmem_src) {
 ZF_DEVICE void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 ZF_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- programmatic dependent launch: lets the next kernel in the stream start while this one is still running
+ZF_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- look-back descriptors: one 64-bit word carries flag + value, so relaxed gpu-scope accesses suffice
 ZF_DEVICE void st_relaxed_gpu(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

@@ -67,6 +67,8 @@ struct FrameJob {
     uint32_t max_rice_order;
     uint32_t max_rice_param;
     uint32_t use_tma;
+    uint32_t pdl_trigger;          // general kernels: release the dependent launch at once (the one-CTA last-frame
+                                   // launch in front of the persistent full-frame kernel)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -1090,6 +1092,7 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_kernel(const Fra
     const uint32_t base = (uint32_t)t * kSpt;
     const bool tma = FULL && job.use_tma;
 
+    if (job.pdl_trigger) pdl_launch_dependents();
     init_tables(c, t);
     if (t < kRawPadWords) sm.raw[t] = 0;
     if (t == 0) {

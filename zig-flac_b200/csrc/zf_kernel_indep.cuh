@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_indep_kernel(const Fram
     SmemCommon &c = sm.c;
     uint32_t *bits = sm.bits;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (job.pdl_trigger) pdl_launch_dependents();
     const uint32_t n = job.block_size;
     const uint32_t nch = job.channels;
     const uint32_t depth = 8u * BYTES;
