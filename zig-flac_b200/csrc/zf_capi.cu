@@ -44,6 +44,7 @@ struct Slot {  // one in-flight batch: device buffers + pinned staging
     uint8_t *h_out = nullptr;   // pinned
     uint32_t *d_sizes = nullptr;
     uint32_t *h_sizes = nullptr;  // pinned
+    unsigned char *d_ctl_block = nullptr;   // one allocation, one memset per batch: [ctl 16 B][tail meta 32 B][pad][descriptors]
     unsigned long long *d_desc = nullptr;
     unsigned int *d_ctl = nullptr;          // [0],[1] tickets, [2] status
     unsigned long long *d_total = nullptr;
@@ -206,8 +207,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     }
     if (frames > e->cfg.max_frames_per_batch) return ZF_ERR_INVALID_ARG;
     if (first_frame_number + frames > (1ull << 31)) return ZF_ERR_UNSUPPORTED;  // header coder is UB upstream (Q16)
-    ZF_CUDA(cudaMemsetAsync(sl.d_desc, 0, sizeof(unsigned long long) * frames, s));
-    ZF_CUDA(cudaMemsetAsync(sl.d_ctl, 0, sizeof(unsigned int) * 4, s));
+    ZF_CUDA(cudaMemsetAsync(sl.d_ctl_block, 0, 64 + sizeof(unsigned long long) * frames, s));  // tickets, status, descriptors
     ZF_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s));
     zf::FrameJob job;
     memset(&job, 0, sizeof job);
@@ -236,7 +236,6 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     const uint32_t ring = sl.kev_count % kRing;
     if (full) ZF_CUDA(cudaEventRecord(sl.kev[2 * ring], s));
     if (split_tail) {
-        ZF_CUDA(cudaMemsetAsync(sl.d_tail_meta, 0, sizeof(unsigned long long) * 4, s));
         zf::FrameJob tj = job;
         tj.pcm = d_pcm + full * e->frame_pcm_bytes;
         tj.out = sl.d_tail;
@@ -311,14 +310,15 @@ int slot_init(zf_encoder *e, Slot &sl) {
     const size_t frames = e->cfg.max_frames_per_batch;
     ZF_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     ZF_CUDA(cudaMalloc(&sl.d_tail, e->max_frame_bytes + 64));
-    ZF_CUDA(cudaMalloc(&sl.d_tail_meta, sizeof(unsigned long long) * 4));
     ZF_CUDA(cudaEventCreate(&sl.ev_start));
     ZF_CUDA(cudaEventCreate(&sl.ev_stop));
     ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
     for (int i = 0; i < 2 * kRing; i++) ZF_CUDA(cudaEventCreate(&sl.kev[i]));
     ZF_CUDA(cudaMalloc(&sl.d_sizes, sizeof(uint32_t) * frames));
-    ZF_CUDA(cudaMalloc(&sl.d_desc, sizeof(unsigned long long) * frames));
-    ZF_CUDA(cudaMalloc(&sl.d_ctl, sizeof(unsigned int) * 4));
+    ZF_CUDA(cudaMalloc(&sl.d_ctl_block, 64 + sizeof(unsigned long long) * frames));
+    sl.d_ctl = reinterpret_cast<unsigned int *>(sl.d_ctl_block);
+    sl.d_tail_meta = reinterpret_cast<unsigned long long *>(sl.d_ctl_block + 16);
+    sl.d_desc = reinterpret_cast<unsigned long long *>(sl.d_ctl_block + 64);
     ZF_CUDA(cudaMalloc(&sl.d_total, sizeof(unsigned long long)));
     ZF_CUDA(cudaMallocHost(&sl.h_sizes, sizeof(uint32_t) * frames));
     ZF_CUDA(cudaMallocHost(&sl.h_total, sizeof(unsigned long long) * 2));
@@ -327,8 +327,8 @@ int slot_init(zf_encoder *e, Slot &sl) {
 
 void slot_free(Slot &sl) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
-    cudaFree(sl.d_tail); cudaFree(sl.d_tail_meta);
-    cudaFree(sl.d_pcm); cudaFree(sl.d_out); cudaFree(sl.d_sizes); cudaFree(sl.d_desc); cudaFree(sl.d_ctl); cudaFree(sl.d_total);
+    cudaFree(sl.d_tail);
+    cudaFree(sl.d_pcm); cudaFree(sl.d_out); cudaFree(sl.d_sizes); cudaFree(sl.d_ctl_block); cudaFree(sl.d_total);
     cudaFreeHost(sl.h_pcm); cudaFreeHost(sl.h_out); cudaFreeHost(sl.h_sizes); cudaFreeHost(sl.h_total);
     if (sl.ev_start) cudaEventDestroy(sl.ev_start);
     if (sl.ev_stop) cudaEventDestroy(sl.ev_stop);
