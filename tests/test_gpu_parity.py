@@ -138,7 +138,7 @@ def test_write_frame_matches_batched_path(zf, oracle, encoders):
 
 @pytest.mark.parametrize("bits,rate", [(16, 44100), (24, 96000), (32, 192000)])
 def test_synthetic_stream_multi_batch(zf, oracle, bits, rate):
-    """BASELINE signal; more frames than one batch so the two-slot pipeline and look-back both run."""
+    """BASELINE signal; more frames than one batch so the three-stage host pipeline and the look-back both run."""
     n = 4096 * 150 + 2048
     pcm = zf.synth_pcm(n, rate, bits)
     with zf.Encoder(zf.Config.default(2, bits), rate, max_frames_per_batch=64) as enc:

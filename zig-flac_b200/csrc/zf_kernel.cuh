@@ -1,12 +1,13 @@
-// zf_kernel.cuh -- the FLAC frame-encode kernels (sm_100a).
+// zf_kernel.cuh -- shared device code and the GENERAL stereo frame-encode kernel (sm_100a): any block size up to 4096,
+// short last frames, any Rice limits, any sample rate.  The dominant kernel for full frames is zf_kernel_v3.cuh.
 //
-// One thread block (256 threads) encodes one frame; a persistent grid pulls frames from an atomic
+// One thread block (512 threads x 8 samples) encodes one frame; a persistent grid pulls frames from an atomic
 // ticket and compacts the variable-length frames into one output stream with a decoupled look-back
 // over frame byte sizes (single pass: FLAC bytes are written to HBM exactly once).
 //
 // Per frame (reference call stack: Encoder.writeFrame, encoder.zig:234-284):
 //   load     raw interleaved PCM -> shared memory by a 1-D TMA bulk copy (next frame prefetched),
-//            unpacked to int32 registers: 16 consecutive samples + 4 history samples per thread
+//            unpacked to int32 registers: 8 consecutive samples + 4 history samples per thread
 //   pass 1   L, R, M=(L+R)>>1, S=L-R: OR of samples (wasted bits, encoder.zig:556-570) and the five
 //            sum|delta^k x| of fixed.bestOrder (fixed.zig:85-167), block-reduced with REDUX
 //   decide   CONSTANT / VERBATIM / fixed order per candidate channel (encoder.zig:482-554)
