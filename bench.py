@@ -274,7 +274,7 @@ def main():
 
     # ---- end to end through the C ABI with pinned host buffers (H2D + encode + D2H every step) ----
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
-    enc2 = zf.Encoder(zf.Config.default(CHANNELS, bits), rate, device_id=local_rank, max_frames_per_batch=1024)
+    enc2 = zf.Encoder(zf.Config.default(CHANNELS, bits), rate, device_id=local_rank, max_frames_per_batch=2048)
     h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
     h_out_np = h_out.numpy()
     h_pcm_np = h_pcm.numpy()
@@ -326,7 +326,7 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": all_pcm,
                     "d2h_bytes_per_step": all_e2e_out, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
-                    "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 1024-frame batches, 3-stage pipeline: upload | encode | download)"},
+                    "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 2048-frame batches, 3-stage pipeline: upload | encode | download)"},
             "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),

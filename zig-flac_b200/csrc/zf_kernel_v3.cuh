@@ -837,6 +837,8 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
     __syncthreads();
     uint32_t phase = 0;
     uint32_t f = sm.next_frame;
+    uint32_t rate_extra;
+    const uint32_t rate_code_v = rate_code(job.sample_rate, rate_extra);  // a table rate: no trailer (checked on the host)
     LbArgs lba;
     lba.desc = job.desc; lba.total_bytes = job.total_bytes; lba.status = job.status; lba.out_cap = job.out_cap;
     lba.batch_frames = job.batch_frames;
@@ -1401,9 +1403,8 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             wa.or_tail();
             wb.or_tail();
             if (warp == kW - 1) {  // frame header, one byte per lane
-                uint32_t hlen, erb;
-                const uint32_t byte = header_byte(sm.crc8tab, lane, frame_number, depth, ch_type,
-                                                  rate_code(job.sample_rate, erb), hlen);
+                uint32_t hlen;
+                const uint32_t byte = header_byte(sm.crc8tab, lane, frame_number, depth, ch_type, rate_code_v, hlen);
                 if ((uint32_t)lane < hlen) {
                     const uint32_t b = lead + (uint32_t)lane;
                     atomicOr(&sm.bits[b >> 2], byte << (24u - 8u * (b & 3u)));
