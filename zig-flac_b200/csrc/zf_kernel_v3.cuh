@@ -753,16 +753,6 @@ ZF_NOINLINE void copy_out(const Smem<BYTES> &sm, uint8_t *out, unsigned long lon
     }
 }
 
-template <int BYTES>
-ZF_DEVICE void zero_bits(Smem<BYTES> &sm, int t, const Pend &P) {
-    uint4 *bz = reinterpret_cast<uint4 *>(sm.bits);
-    const uint4 z = {0, 0, 0, 0};
-    const uint32_t nwords = (P.lead + P.fbytes) >> 2;
-    const uint32_t n4 = P.fits ? ((nwords + 2u + 3u) >> 2) : (uint32_t)(BitBufWords<BYTES>::value + 8) / 4u;
-#pragma unroll 1
-    for (uint32_t k = t; k < n4; k += kT) bz[k] = z;
-}
-
 // Frame header (frame_writer.zig:151-265) + CRC-8 (:128-141), one byte per lane of one warp.  Covers what this kernel
 // is launched for: block size 4096 (code 12, no trailer), a sample rate from the table (codes 1..11, no trailer),
 // frame numbers below 2^31.  Returns this lane's byte; `len` is the header length including the CRC-8.
@@ -1257,11 +1247,9 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             while (!sm.lb_done) lb_step(sm, lba, lane, P);
         }
         __syncthreads();
-        if (P.valid) {  // the previous frame leaves the bit buffer
-            copy_out(sm, job.out, job.out_cap, t, P);
-            __syncthreads();
-            zero_bits(sm, t, P);  // ordered before the first stored codeword by the scan's barrier
-        }
+        // the previous frame leaves the bit buffer (the scan's barrier orders these reads before the next stores; the
+        // buffer is not cleared: see below)
+        if (P.valid) copy_out(sm, job.out, job.out_cap, t, P);
         // ---- every warp: partition order per candidate (rice.zig:262-276: '<=' keeps the highest order on ties),
         //      FIXED only with a strictly smaller estimate than VERBATIM (encoder.zig:538), then the stereo mode:
         //      first minimum of [L+R, L+S, S+R, M+S] (encoder.zig:441-452).  Results are uniform over the block. ----
@@ -1357,6 +1345,14 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         wa.init(sm.bits, 8u * lead + hdr_bits + ex_a);
         wb.init(sm.bits, 8u * lead + hdr_bits + tot_a + ex_b);
         if (fits) {
+            // Every word that some thread completes is stored whole; only words nobody completes depend on their old
+            // content, because they only receive ORs (after the next barrier): the words in front of the first subframe
+            // bit (leading zero bytes, frame header) and the frame's last word if it is partial.  Clear exactly those.
+            {
+                const uint32_t first_bit = 8u * lead + hdr_bits, end_bit = 8u * lead + total_bits;
+                if ((uint32_t)t < (first_bit >> 5)) sm.bits[t] = 0;               // at most 8 words
+                if (t == kT - 1 && (end_bit & 31u)) sm.bits[end_bit >> 5] = 0;
+            }
 #pragma unroll 1
             for (int ch = 0; ch < 2; ch++) {  // one copy of the header writer
                 BitW w = ch ? wb : wa;
