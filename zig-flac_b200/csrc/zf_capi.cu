@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <vector>
 
@@ -34,7 +35,9 @@ thread_local char g_cuda_err[256] = "";
     } while (0)
 
 constexpr int kPow8Len = 1 << 18;
-constexpr int kSlots = 3;  // upload of batch b+1, kernels of batch b and download of batch b-1 overlap
+constexpr int kSlots = 4;  // upload of batch b+1, kernels of batch b and downloads of batches b-1, b-2 overlap: a batch's
+                           // buffers are held until its download has arrived, and the host must not wait for that before
+                           // it queues the next upload
 constexpr int kRing = 256;  // covers the largest frame of the multi-channel path (8 ch x 4096 x 33 bits)
 
 struct Slot {  // one in-flight batch: device buffers + pinned staging
@@ -53,6 +56,7 @@ struct Slot {  // one in-flight batch: device buffers + pinned staging
     uint8_t *d_tail = nullptr;               // private output of the last-frame launch
     unsigned long long *d_tail_meta = nullptr;  // [0] desc, [1] total, [2] lo32: frame size
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_down = nullptr;  // upload / download finished: keep the batches' copies in order
     cudaEvent_t kev[2 * kRing] = {};  // start/stop pairs around the full-frame kernel of recent batches
     uint32_t kev_count = 0;           // pairs recorded since the last zf_kernel_times()
     size_t pcm_cap = 0, out_cap = 0;
@@ -60,6 +64,7 @@ struct Slot {  // one in-flight batch: device buffers + pinned staging
     bool busy = false;      // kernels submitted, results not fetched yet
     bool draining = false;  // output copy in flight
     uint8_t *copy_dst = nullptr;  // pageable destination of the staged output copy
+    uint32_t *sizes_dst = nullptr;  // caller's frame_sizes (filled from the pinned copy when the download has arrived)
     size_t copy_len = 0;
     bool have_io = false;
 };
@@ -73,6 +78,7 @@ struct zf_encoder {
     float kernel_ms_last = 0.f;
     uint16_t *d_pow8 = nullptr;
     Slot slot[kSlots];  // submit/collect use slot 0 only; zf_encode_pcm rotates through all of them
+    cudaStream_t s_up = nullptr, s_down = nullptr;  // all uploads / all downloads, each in batch order on its own stream
     size_t frame_pcm_bytes = 0;
     size_t max_frame_bytes = 0;
     bool stereo = false;
@@ -81,9 +87,28 @@ struct zf_encoder {
     size_t smem_stereo = 0;
     size_t smem_v3 = 0;
     size_t smem_indep = 0;
+    // ZF_TRACE=1 (development aid): per-batch device timeline of zf_encode_pcm, printed to stderr
+    bool trace = false;
+    bool no_taper = false;
+    std::vector<cudaEvent_t> tr_ev;  // [batch][kTracePoints]
+    std::vector<double> tr_host;     // [batch][3]: submit returned, fetch returned, finish returned (ms)
+    std::chrono::steady_clock::time_point tr_h0;
+    uint64_t tr_batch = 0;
 };
 
 namespace {
+
+enum { kTrUp0 = 0, kTrUp1, kTrKern1, kTrSmall1, kTrDown0, kTrDown1, kTracePoints };
+void tr_mark(zf_encoder *e, cudaStream_t s, int point) {
+    if (!e->trace) return;
+    const size_t i = e->tr_batch * kTracePoints + point;
+    if (i < e->tr_ev.size()) cudaEventRecord(e->tr_ev[i], s);
+}
+void tr_host(zf_encoder *e, uint64_t batch, int point) {
+    if (!e->trace || batch * 3 + point >= e->tr_host.size()) return;
+    e->tr_host[batch * 3 + point] =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - e->tr_h0).count();
+}
 
 bool depth_ok(unsigned d) { return d == 16 || d == 24 || d == 32; }
 
@@ -313,6 +338,8 @@ int slot_init(zf_encoder *e, Slot &sl) {
     ZF_CUDA(cudaEventCreate(&sl.ev_start));
     ZF_CUDA(cudaEventCreate(&sl.ev_stop));
     ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming));
+    ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_down, cudaEventDisableTiming));
     for (int i = 0; i < 2 * kRing; i++) ZF_CUDA(cudaEventCreate(&sl.kev[i]));
     ZF_CUDA(cudaMalloc(&sl.d_sizes, sizeof(uint32_t) * frames));
     ZF_CUDA(cudaMalloc(&sl.d_ctl_block, 64 + sizeof(unsigned long long) * frames));
@@ -333,6 +360,8 @@ void slot_free(Slot &sl) {
     if (sl.ev_start) cudaEventDestroy(sl.ev_start);
     if (sl.ev_stop) cudaEventDestroy(sl.ev_stop);
     if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    if (sl.ev_up) cudaEventDestroy(sl.ev_up);
+    if (sl.ev_down) cudaEventDestroy(sl.ev_down);
     for (int i = 0; i < 2 * kRing; i++) if (sl.kev[i]) cudaEventDestroy(sl.kev[i]);
     if (sl.stream) cudaStreamDestroy(sl.stream);
     sl = Slot();
@@ -348,6 +377,16 @@ bool is_pinned_or_device_visible(const void *p) {
 }
 
 // H2D + kernels + D2H of the small results for one batch held in a slot (asynchronous).
+// The two words the host needs before it can start the download (bytes produced, status flags) go straight to pinned host
+// memory: a copy-engine transfer of 12 bytes took 20-115 us while the link was busy with the next upload.
+__global__ void zf_publish_kernel(const unsigned long long *d_total, const unsigned int *d_status, unsigned long long *h_pub) {
+    h_pub[0] = *d_total;
+    h_pub[1] = *d_status;
+}
+
+// Upload (upload stream) + kernels (the slot's stream) for one batch held in a slot (asynchronous).  Uploads and downloads
+// of all batches each run in order on a stream of their own: issued on per-slot streams, copies of both directions blocked
+// one another on the copy engines (an upload waited for the download of the batch two before it).
 int slot_submit(zf_encoder *e, Slot &sl, const uint8_t *pcm, uint64_t samples, uint64_t first_frame_number) {
     int rc = ensure_io(e, sl);
     if (rc) return rc;
@@ -360,18 +399,23 @@ int slot_submit(zf_encoder *e, Slot &sl, const uint8_t *pcm, uint64_t samples, u
         memcpy(sl.h_pcm, pcm, bytes);
         src = sl.h_pcm;
     }
-    if (bytes) ZF_CUDA(cudaMemcpyAsync(sl.d_pcm, src, bytes, cudaMemcpyHostToDevice, sl.stream));
+    tr_mark(e, e->s_up, kTrUp0);
+    if (bytes) ZF_CUDA(cudaMemcpyAsync(sl.d_pcm, src, bytes, cudaMemcpyHostToDevice, e->s_up));
+    ZF_CUDA(cudaEventRecord(sl.ev_up, e->s_up));
+    tr_mark(e, e->s_up, kTrUp1);
+    ZF_CUDA(cudaStreamWaitEvent(sl.stream, sl.ev_up, 0));
     ZF_CUDA(cudaEventRecord(sl.ev_start, sl.stream));
     int launches = 0;
     rc = launch_batch(e, sl, sl.d_pcm, samples, first_frame_number, sl.d_out, sl.out_cap, sl.d_sizes, sl.d_total, sl.stream,
                       &launches);
     if (rc) return rc;
     ZF_CUDA(cudaEventRecord(sl.ev_stop, sl.stream));
-    e->launches_last = launches;
-    if (frames) ZF_CUDA(cudaMemcpyAsync(sl.h_sizes, sl.d_sizes, sizeof(uint32_t) * frames, cudaMemcpyDeviceToHost, sl.stream));
-    ZF_CUDA(cudaMemcpyAsync(sl.h_total, sl.d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.stream));
-    ZF_CUDA(cudaMemcpyAsync(sl.h_total + 1, sl.d_ctl + 2, sizeof(unsigned int), cudaMemcpyDeviceToHost, sl.stream));
+    tr_mark(e, sl.stream, kTrKern1);
+    e->launches_last = launches + 1;
+    zf_publish_kernel<<<1, 1, 0, sl.stream>>>(sl.d_total, sl.d_ctl + 2, sl.h_total);
+    ZF_CUDA(cudaGetLastError());
     ZF_CUDA(cudaEventRecord(sl.ev_done, sl.stream));
+    tr_mark(e, sl.stream, kTrSmall1);
     sl.frames = (uint32_t)frames;
     sl.busy = true;
     return ZF_OK;
@@ -396,18 +440,23 @@ int slot_fetch(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *ou
     if (out_len) *out_len = total;
     if (sl.frames > frame_sizes_cap) return ZF_ERR_OUT_TOO_SMALL;
     if (total > out_cap) return ZF_ERR_OUT_TOO_SMALL;
-    if (frame_sizes) memcpy(frame_sizes, sl.h_sizes, sizeof(uint32_t) * sl.frames);
     sl.copy_dst = nullptr;
     sl.copy_len = 0;
+    sl.sizes_dst = frame_sizes;
+    tr_mark(e, e->s_down, kTrDown0);
     if (total) {
         if (is_pinned_or_device_visible(out)) {
-            ZF_CUDA(cudaMemcpyAsync(out, sl.d_out, total, cudaMemcpyDeviceToHost, sl.stream));
+            ZF_CUDA(cudaMemcpyAsync(out, sl.d_out, total, cudaMemcpyDeviceToHost, e->s_down));
         } else {  // pageable caller memory: through the pinned staging buffer, copied on in slot_finish
-            ZF_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, sl.stream));
+            ZF_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, e->s_down));
             sl.copy_dst = out;
             sl.copy_len = total;
         }
     }
+    if (frame_sizes && sl.frames)
+        ZF_CUDA(cudaMemcpyAsync(sl.h_sizes, sl.d_sizes, sizeof(uint32_t) * sl.frames, cudaMemcpyDeviceToHost, e->s_down));
+    ZF_CUDA(cudaEventRecord(sl.ev_down, e->s_down));
+    tr_mark(e, e->s_down, kTrDown1);
     sl.draining = true;
     return ZF_OK;
 }
@@ -416,7 +465,8 @@ int slot_fetch(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *ou
 int slot_finish(zf_encoder *, Slot &sl) {
     if (!sl.draining) return ZF_OK;
     sl.draining = false;
-    ZF_CUDA(cudaStreamSynchronize(sl.stream));
+    ZF_CUDA(cudaEventSynchronize(sl.ev_down));
+    if (sl.sizes_dst && sl.frames) memcpy(sl.sizes_dst, sl.h_sizes, sizeof(uint32_t) * sl.frames);
     if (sl.copy_dst && sl.copy_len) memcpy(sl.copy_dst, sl.h_out, sl.copy_len);
     return ZF_OK;
 }
@@ -495,6 +545,8 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     e->cfg = *cfg;
     e->stereo = cfg->channels == 2 && cfg->stereo_decorrelation;
     { const char *lg = getenv("ZF_LEGACY_KERNEL"); e->force_legacy = lg && lg[0] == '1'; }
+    { const char *tr = getenv("ZF_TRACE"); e->trace = tr && tr[0] == '1'; }
+    { const char *nt = getenv("ZF_NO_TAPER"); e->no_taper = nt && nt[0] == '1'; }  // A/B of the batch plan (development aid)
     e->frame_pcm_bytes = (size_t)cfg->block_size * cfg->channels * (cfg->bit_depth / 8);
     e->max_frame_bytes = max_frame_bytes_of(cfg);
     cudaDeviceProp prop;
@@ -502,6 +554,9 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     e->sm_count = prop.multiProcessorCount;
     rc = setup_kernels(e);
     for (int i = 0; i < kSlots && !rc; i++) rc = slot_init(e, e->slot[i]);
+    if (!rc && (cudaStreamCreateWithFlags(&e->s_up, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&e->s_down, cudaStreamNonBlocking) != cudaSuccess))
+        rc = ZF_ERR_CUDA;
     if (!rc) {
         std::vector<uint16_t> pw(kPow8Len);
         uint32_t v = 1;
@@ -527,8 +582,13 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
 void zf_encoder_destroy(zf_encoder *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device_id);
+    if (e->s_up) cudaStreamSynchronize(e->s_up);
+    if (e->s_down) cudaStreamSynchronize(e->s_down);
     for (int i = 0; i < kSlots; i++) slot_free(e->slot[i]);
+    if (e->s_up) cudaStreamDestroy(e->s_up);
+    if (e->s_down) cudaStreamDestroy(e->s_down);
     cudaFree(e->d_pow8);
+    for (cudaEvent_t ev : e->tr_ev) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -558,7 +618,23 @@ int zf_encode_pcm(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channe
     if (out_len) *out_len = 0;
     if (frames > frame_sizes_cap && frame_sizes) return ZF_ERR_OUT_TOO_SMALL;
     const uint64_t per = e->cfg.max_frames_per_batch;
-    const uint64_t nbatch = (frames + per - 1) / per;
+    // Batch plan: full batches while more than one batch is left, then halves down to kMinTailBatch frames.  What follows
+    // the last upload -- that batch's kernels and its download -- is not overlapped with anything, so it is kept short.
+    std::vector<uint64_t> first;  // first frame of every batch, then the frame count
+    {
+        const uint64_t kMinTailBatch = 256;
+        const bool taper = !e->no_taper;
+        uint64_t f = 0;
+        while (f < frames) {
+            const uint64_t left = frames - f;
+            uint64_t n = std::min(left, per);
+            if (taper && left <= per && left > 2 * kMinTailBatch) n = (left + 1) / 2;
+            first.push_back(f);
+            f += n;
+        }
+        first.push_back(frames);
+    }
+    const uint64_t nbatch = first.size() - 1;
     const size_t ic_bytes = (size_t)e->cfg.channels * (e->cfg.bit_depth / 8);
     size_t pos = 0;
     float ms = 0.f;
@@ -568,30 +644,58 @@ int zf_encode_pcm(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channe
         cudaDeviceSynchronize();
         return rc;
     };
-    // three-stage pipeline over the slots: batch b uploads and encodes while batch b-1's output is on its way back
-    // and batch b-2's arrival is awaited
-    for (uint64_t b = 0; b < nbatch + 2; b++) {
+    if (e->trace) {
+        for (cudaEvent_t ev : e->tr_ev) cudaEventDestroy(ev);
+        e->tr_ev.assign(nbatch * kTracePoints, nullptr);
+        for (cudaEvent_t &ev : e->tr_ev) cudaEventCreate(&ev);
+        e->tr_host.assign(nbatch * 3, 0.0);
+        e->tr_h0 = std::chrono::steady_clock::now();
+    }
+    // pipeline over the slots: batch b is queued (upload, kernels), batch b-1's kernels are awaited and its download is
+    // queued, and the arrival of the oldest batch in flight frees the slot for batch b+1
+    constexpr uint64_t kLag = kSlots - 1;
+    for (uint64_t b = 0; b < nbatch + kLag; b++) {
         if (b < nbatch) {
-            const uint64_t f0 = b * per;
+            const uint64_t f0 = first[b];
             const uint64_t s0 = f0 * bs;
-            const uint64_t ns = std::min<uint64_t>(per * bs, samples_per_channel - s0);
+            const uint64_t ns = std::min<uint64_t>((first[b + 1] - f0) * bs, samples_per_channel - s0);
+            e->tr_batch = b;
             int rc = slot_submit(e, e->slot[b % kSlots], pcm + s0 * ic_bytes, ns, first_frame_number + f0);
             if (rc) return fail(rc);
+            tr_host(e, b, 0);
             launches += e->launches_last;
         }
         if (b >= 1 && b - 1 < nbatch) {
-            const uint64_t f0 = (b - 1) * per;
+            const uint64_t f0 = first[b - 1];
             size_t got = 0;
             uint32_t nf = 0;
+            e->tr_batch = b - 1;
             int rc = slot_fetch(e, e->slot[(b - 1) % kSlots], out + pos, out_cap - pos, &got,
                                 frame_sizes ? frame_sizes + f0 : nullptr, frame_sizes ? (uint32_t)(frames - f0) : 0xffffffffu, &nf);
             if (rc) return fail(rc);
             pos += got;
             ms += e->kernel_ms_last;
+            tr_host(e, b - 1, 1);
         }
-        if (b >= 2) {
-            int rc = slot_finish(e, e->slot[(b - 2) % kSlots]);
+        if (b >= kLag) {
+            int rc = slot_finish(e, e->slot[(b - kLag) % kSlots]);
             if (rc) return fail(rc);
+            tr_host(e, b - kLag, 2);
+        }
+    }
+    if (e->trace && nbatch) {
+        static const char *names[kTracePoints] = {"up0", "up1", "kern1", "small1", "down0", "down1"};
+        fprintf(stderr, "[zf trace] %llu batches; device times relative to batch 0 up0, host times relative to the call (ms)\n",
+                (unsigned long long)nbatch);
+        for (uint64_t b = 0; b < nbatch; b++) {
+            fprintf(stderr, "[zf trace] batch %2llu:", (unsigned long long)b);
+            for (int k = 0; k < kTracePoints; k++) {
+                float t = 0.f;
+                cudaEventElapsedTime(&t, e->tr_ev[0], e->tr_ev[b * kTracePoints + k]);
+                fprintf(stderr, " %s %.3f", names[k], t);
+            }
+            fprintf(stderr, " | host submit %.3f fetch %.3f finish %.3f\n", e->tr_host[b * 3], e->tr_host[b * 3 + 1],
+                    e->tr_host[b * 3 + 2]);
         }
     }
     e->kernel_ms_last = ms;
