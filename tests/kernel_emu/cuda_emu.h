@@ -128,6 +128,7 @@ static inline void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsig
 static inline void cp_async16_cg(void *dst, const void *src) { memcpy(dst, src, 16); }
 static inline void cp_async_commit() {}
 static inline void pdl_launch_dependents() {}
+static inline void pdl_wait_primary() {}
 static inline void cp_async_wait_all() {}
 static inline void st_relaxed_gpu(unsigned long long *p, unsigned long long v) { *p = v; }
 static inline unsigned long long ld_relaxed_gpu(const unsigned long long *p) { return *p; }

@@ -65,6 +65,22 @@ def test_short_last_frames(zf, oracle, encoders, bits):
         _compare(oracle, enc, pcm2, L2.size, 2, bits, 44100)
 
 
+def test_long_short_frame_behind_one_full_frame_repeated(zf, oracle, encoders):
+    # the short-frame launch (one CTA, up to 4095 samples) outlasts the one-frame persistent kernel that is launched as its
+    # programmatic dependent; the append step must still see the finished short frame, every time
+    enc = encoders(2, 24)
+    rng = np.random.default_rng(99)
+    n = 4096 + 4095
+    x = rng.integers(-(1 << 22), 1 << 22, size=(n, 2), dtype=np.int64)
+    pcm = oracle.pcm_bytes_from_int(x.reshape(-1), 24)
+    cfg = oracle.config(2, 24)
+    ref, ref_sizes = oracle.encode_pcm(pcm, n, cfg, 44100, 0)
+    for _ in range(40):
+        got, got_sizes = enc.encode_pcm(pcm, n, 0)
+        assert np.array_equal(ref_sizes, got_sizes)
+        assert ref.tobytes() == got.tobytes()
+
+
 @pytest.mark.parametrize("bits", [16, 24])
 def test_frame_numbers_and_sample_rates(zf, oracle, encoders, bits):
     rng = np.random.default_rng(5)

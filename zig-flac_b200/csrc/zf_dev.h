@@ -63,6 +63,9 @@ ZF_DEVICE void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memo
 
 // ---- programmatic dependent launch: lets the next kernel in the stream start while this one is still running
 ZF_DEVICE void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// A kernel launched as a programmatic dependent executes this once before it ends, so that its own completion implies that
+// of the kernel in front of it (whose output the kernel after it reads); without such a launch it returns at once.
+ZF_DEVICE void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- look-back descriptors: one 64-bit word carries flag + value, so relaxed gpu-scope accesses suffice
 ZF_DEVICE void st_relaxed_gpu(unsigned long long *p, unsigned long long v) {

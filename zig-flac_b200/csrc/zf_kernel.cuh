@@ -1245,6 +1245,7 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_kernel(const Fra
         if (t == 0) c.cur_frame = c.next_frame;
         __syncthreads();
     }
+    if (t == 0) pdl_wait_primary();
 }
 
 // ---------------------------------------------------------------------------------------------------

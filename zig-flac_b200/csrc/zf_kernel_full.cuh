@@ -425,6 +425,7 @@ __global__ void __launch_bounds__(kThreads, BYTES == 4 ? 1 : 2) zf_encode_stereo
         if (t == 0) c.cur_frame = c.next_frame;
         __syncthreads();
     }
+    if (t == 0) pdl_wait_primary();
 }
 
 }  // namespace zf

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_indep_kernel(const Fram
         if (t == 0) c.cur_frame = c.next_frame;
         __syncthreads();
     }
+    if (t == 0) pdl_wait_primary();
 }
 
 }  // namespace zf

@@ -1455,6 +1455,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         __syncthreads();
         copy_out(sm, job.out, job.out_cap, t, P);
     }
+    if (t == 0) pdl_wait_primary();
 }
 
 }  // namespace v3
