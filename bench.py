@@ -326,7 +326,7 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": all_pcm,
                     "d2h_bytes_per_step": all_e2e_out, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
-                    "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 2048-frame batches, 3-stage pipeline: upload | encode | download)"},
+                    "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 2048-frame batches, pipeline: upload | encode | download on three streams)"},
             "gpu_launches": args.steps * launches_per_step,
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
