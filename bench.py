@@ -296,10 +296,11 @@ def main():
     same = bool((d_out[:flac_bytes].cpu().numpy() == got).all()) and flac_bytes == int(got.size)
 
     # totals over ranks
-    tot = torch.tensor([nsamples, flac_bytes, pcm_bytes, e2e_out_bytes], dtype=torch.int64, device=dev)
+    tot = torch.tensor([nsamples, flac_bytes, pcm_bytes, e2e_out_bytes, args.steps * launches_per_step], dtype=torch.int64,
+                       device=dev)
     if dist is not None:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    all_samples, all_flac, all_pcm, all_e2e_out = [int(v) for v in tot.tolist()]
+    all_samples, all_flac, all_pcm, all_e2e_out, all_launches = [int(v) for v in tot.tolist()]
 
     if rank == 0:
         value = all_samples * CHANNELS / (ms_step * 1e-3) / 1e6
@@ -327,7 +328,7 @@ def main():
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": all_pcm,
                     "d2h_bytes_per_step": all_e2e_out, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
                     "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 2048-frame batches, pipeline: upload | encode | download on three streams)"},
-            "gpu_launches": args.steps * launches_per_step,
+            "gpu_launches": all_launches,  # all ranks, timed region of the device-resident arm
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
                          "kernel": ("zf::v3::zf_encode_stereo_v3_kernel<%d>" % (bits // 8)) if not os.environ.get("ZF_LEGACY_KERNEL") else ("zf::zf_encode_stereo_full_kernel<%d>" % (bits // 8)),
