@@ -1417,16 +1417,20 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 for (uint32_t j = (uint32_t)t; j * (uint32_t)kCrcChunkWords < nwords_crc; j += kT) {
                     const uint32_t end = nwords_crc - j * (uint32_t)kCrcChunkWords;  // exclusive
                     uint32_t a = 0;
+                    // x^(8 * bytes after the chunk) mod P: an L2 round trip, started before the words are folded
+                    const uint32_t pw = job.pow8[j * (uint32_t)kCrcChunkWords * 4u];
                     if (end >= (uint32_t)kCrcChunkWords) {
                         const uint4 *p = reinterpret_cast<const uint4 *>(sm.bits + (end - (uint32_t)kCrcChunkWords));
+                        uint4 v = p[0];
 #pragma unroll 1
-                        for (int k = 0; k < kCrcChunkWords / 4; k++) {
-                            const uint4 v = p[k];
+                        for (int k = 1; k <= kCrcChunkWords / 4; k++) {
+                            const uint4 nx = p[k];  // next four words meanwhile (the last trip reads into the padding)
                             a = q_fold((a << 4) ^ (a << 2) ^ v.x);
                             a = q_fold((a << 4) ^ (a << 2) ^ v.y);
                             a = q_fold((a << 4) ^ (a << 2) ^ v.z);
                             a = q_fold((a << 4) ^ (a << 2) ^ v.w);
                             par ^= v.x ^ v.y ^ v.z ^ v.w;
+                            v = nx;
                         }
                     } else {
                         for (uint32_t k = 0; k < end; k++) {
@@ -1435,8 +1439,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                             par ^= v;
                         }
                     }
-                    a = q_fold(a);                                                    // < 2^15
-                    const uint32_t pw = job.pow8[j * (uint32_t)kCrcChunkWords * 4u];  // x^(8 * bytes after the chunk) mod P
+                    a = q_fold(a);  // < 2^15
                     acc_q ^= q_mulmod(a, q_fold(pw));
                 }
             }
