@@ -259,3 +259,52 @@ def test_error_behaviour(zf, oracle):
         depth = kw.pop("bit_depth")
         with pytest.raises(zf.FlacGpuError):
             zf.Encoder(zf.Config(2, depth, **kw), rate)
+
+
+@pytest.mark.parametrize("bits", [16, 24, 32])
+def test_patchwork_stream_many_frames_per_cta(zf, oracle, bits):
+    """Frames of wildly different sizes follow one another in every CTA (silence, constants, tones, noise at random levels,
+    full scale, wasted bits): the bit buffer is not cleared between frames, so stale words of a long frame lie behind a
+    short one."""
+    rng = np.random.default_rng(1000 + bits)
+    F = 1 << (bits - 1)
+    frames = 1800  # about four frames per CTA of the persistent kernel
+    seg = []
+    total = 0
+    while total < frames * 4096 + 1234:
+        m = int(rng.integers(300, 3 * 4096))
+        kind = int(rng.integers(0, 8))
+        amp = float(F) * 10.0 ** float(rng.uniform(-4.5, 0))
+        t = np.arange(m)
+        if kind == 0:
+            L = np.zeros(m, dtype=np.int64); R = np.zeros(m, dtype=np.int64)
+        elif kind == 1:
+            L = np.full(m, int(rng.integers(-F, F)), dtype=np.int64); R = np.full(m, int(rng.integers(-F, F)), dtype=np.int64)
+        elif kind == 2:
+            L = (amp * 0.9 * np.sin(t * rng.uniform(0.001, 0.5))).astype(np.int64); R = (L * rng.uniform(-1, 1)).astype(np.int64)
+        elif kind == 3:
+            L = rng.integers(-F, F, m, dtype=np.int64); R = rng.integers(-F, F, m, dtype=np.int64)  # full-scale noise
+        elif kind == 4:
+            L = rng.normal(0, amp / 4, m).astype(np.int64); R = L + rng.integers(-2, 3, m)
+        elif kind == 5:
+            sh = int(rng.integers(1, bits - 2))
+            L = (rng.integers(-F, F, m, dtype=np.int64) >> sh) << sh; R = (rng.integers(-F, F, m, dtype=np.int64) >> sh) << sh
+        elif kind == 6:
+            L = np.cumsum(rng.integers(-3, 4, m)).astype(np.int64); R = -L
+        else:
+            L = np.where(rng.random(m) < 0.01, rng.integers(-F, F, m, dtype=np.int64), 0); R = L[::-1].copy()
+        seg.append((np.clip(L, -F, F - 1), np.clip(R, -F, F - 1)))
+        total += m
+    L = np.concatenate([a for a, _ in seg]); R = np.concatenate([b for _, b in seg])
+    n = L.size
+    pcm = oracle.pcm_bytes_from_int(signals.interleave([L, R]), bits)
+    cfg = oracle.config(2, bits)
+    ref, ref_sizes = oracle.encode_pcm(pcm, n, cfg, 48000, 0)
+    enc = zf.Encoder(zf.Config.default(2, bits), 48000, max_frames_per_batch=4096)
+    try:
+        for _ in range(2):
+            got, got_sizes = enc.encode_pcm(pcm, n, 0)
+            assert np.array_equal(ref_sizes, got_sizes)
+            assert ref.tobytes() == got.tobytes()
+    finally:
+        enc.close()
