@@ -101,6 +101,17 @@ ZF_DEVICE uint32_t shl32(uint32_t v, uint32_t s) {
 #endif
 }
 
+// shr.b32 semantics: shift counts >= 32 give 0
+ZF_DEVICE uint32_t shr32(uint32_t v, uint32_t s) {
+#ifdef ZF_HOST_EMU
+    return s >= 32u ? 0u : (v >> s);
+#else
+    uint32_t d;
+    asm("shr.b32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(s));
+    return d;
+#endif
+}
+
 // WHICH: 0 both channels, 1 left only, 2 right only (the other array is left untouched)
 template <int BYTES, int WHICH>
 ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (&R)[kXn]) {
@@ -453,8 +464,8 @@ struct Sub {
     bool at_start;
 };
 
-// One subframe, counting side.  Fills v[] with what the writing side needs (zigzagged residuals for FIXED, shifted
-// samples for VERBATIM) and returns this thread's bit count.  frame_writer.zig:269-372.
+// One subframe, counting side.  Fills v[] with what the writing side needs (zigzagged residuals for FIXED, plain residuals
+// where the partition is escaped, shifted samples for VERBATIM) and returns this thread's bit count.  frame_writer.zig:269-372.
 template <int BYTES>
 ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u, uint32_t (&v)[kS]) {
     u.choice = 0;
@@ -476,15 +487,21 @@ ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u
         return (uint32_t)kS * u.bps + (t == 0 ? 8u + u.waste : 0u);
     }
     diff_in_place(x, u.order);
-#pragma unroll
-    for (int j = 0; j < kS; j++) v[j] = zigzag((int32_t)(x[kH + j] >> u.waste));  // low 32 bits, fixed.zig:70-73
     const uint32_t sh = 8u - u.po;  // threads per partition = 1 << sh
     u.choice = sm.choice[slot][(1u << u.po) + ((uint32_t)t >> sh)];
     u.at_start = ((uint32_t)t & ((1u << sh) - 1u)) == 0;
+    const bool esc = (u.choice & 0x80u) != 0;
+    {   // zigzagged residuals (low 32 bits, fixed.zig:70-73); an escaped partition keeps them as they are (:341-354)
+        const uint32_t zs = esc ? 0u : 1u, zm = esc ? 0u : 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < kS; j++) {
+            const int32_t r = (int32_t)(x[kH + j] >> u.waste);
+            v[j] = ((uint32_t)r << zs) ^ ((uint32_t)(r >> 31) & zm);
+        }
+    }
     const uint32_t jstart = (t == 0) ? u.order : 0u;
     const uint32_t cnt = (uint32_t)kS - jstart;
     uint32_t bits = (t == 0) ? 8u + u.waste + u.order * u.bps + 6u : 0u;
-    const bool esc = (u.choice & 0x80u) != 0;
     if (u.at_start) bits += 4u + u.method + (esc ? 5u : 0u);
     if (__builtin_expect(esc, 0)) return bits + (u.choice & 0x7fu) * cnt;
     uint32_t qs = 0, mq = 0;
@@ -550,18 +567,12 @@ ZF_DEVICE void sub_head(BitW &bw, const TT (&warm)[4], int t, const Sub &u) {
     }
 }
 
-// this thread's residuals / samples, any kind (the common FIXED non-escape case of both subframes at once is
-// handled by the caller)
+// One subframe's fields of this thread where a codeword may not fit one 32-bit field (long unary run) or the samples have
+// 33 bits (VERBATIM 32-bit side channel); the caller's branch-free loop handles everything else.  Field parameters as there.
 template <bool WIDE>
-ZF_DEVICE void sub_body(BitW &bw, int t, const Sub &u, const uint32_t (&v)[kS]) {
-    if (u.kind == kConstant) return;
-    // rare paths: compact code (a 4-trip loop; v[] must stay in registers, so select instead of indexing)
-    const bool verb = u.kind == kVerbatim, esc = !verb && (u.choice & 0x80u);
-    const uint32_t jstart = (t == 0 && !verb) ? u.order : 0u;
-    const uint32_t wd = verb ? u.bps : (u.choice & 0x7fu);  // raw field width of VERBATIM samples / escaped residuals
-    if ((verb || esc) && wd == 0) return;
-    const uint32_t rawmask = (WIDE && wd >= 32u) ? 0xffffffffu : (0xffffffffu >> (32u - (wd ? wd : 1u)));
-    const uint32_t k = u.choice & 31u, one = 1u << k, m = one - 1u, len = k + 1u;
+ZF_DEVICE void sub_body(BitW &bw, const Sub &u, const uint32_t (&v)[kS], uint32_t k, uint32_t one, uint32_t m, uint32_t len0,
+                        uint32_t jstart) {
+    // rare path: compact code (a 4-trip loop; v[] must stay in registers, so select instead of indexing)
 #pragma unroll 1
     for (int j0 = 0; j0 < kS; j0 += 4) {
 #pragma unroll
@@ -571,16 +582,12 @@ ZF_DEVICE void sub_body(BitW &bw, int t, const Sub &u, const uint32_t (&v)[kS]) 
             z = j0 == 8 ? v[8 + jj] : z;
             z = j0 == 12 ? v[12 + jj] : z;
             if ((uint32_t)(j0 + jj) >= jstart) {
-                if (verb) {                                                               // :282-301
-                    if (WIDE && wd > 32u) {  // 33-bit samples of the 32-bit side channel
-                        bw.put((u.vhi >> (j0 + jj)) & 1u, 1);
-                        bw.put(z, 32);
-                    } else {
-                        bw.put(z & rawmask, wd);
-                    }
+                if (WIDE && len0 > 32u) {  // :282-301, 33-bit samples
+                    bw.put((u.vhi >> (j0 + jj)) & 1u, 1);
+                    bw.put(z, 32);
+                } else {
+                    bw.put_code(shr32(z, k), one | (z & m), len0);
                 }
-                else if (esc) bw.put(((z >> 1) ^ (0u - (z & 1u))) & rawmask, wd);         // :341-354, zigzag undone
-                else bw.put_code(z >> k, one | (z & m), len);                             // :363-372
             }
         }
     }
@@ -1367,23 +1374,35 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 if (ch) wb = w;
                 else wa = w;
             }
-            const uint32_t lena = ua.choice + 1u, lenb = ub.choice + 1u;
-            const bool fast = ua.kind == kFixed && ub.kind == kFixed && !((ua.choice | ub.choice) & 0x80u) &&
-                              ua.maxq + lena <= 32u && ub.maxq + lenb <= 32u;
-            if (__builtin_expect(fast, 1)) {  // every codeword is one field of at most 32 bits: two independent chains, no branches
-                const uint32_t ka = ua.choice, onea = 1u << ka, ma = onea - 1u;
-                const uint32_t kb = ub.choice, oneb = 1u << kb, mb = oneb - 1u;
-                const uint32_t ja = (t == 0) ? ua.order : 0u, jb = (t == 0) ? ub.order : 0u;
-                // :363-372: q zeros, a one, k remainder bits.  Four trips over one piece of code (the arrays rotate by
-                // four registers per trip): code size counts as much as instruction count here
+            // One field per sample: a Rice codeword (:363-372: q zeros, a one, k remainder bits), or w raw bits where the
+            // partition is escaped (:341-354) or the subframe VERBATIM (:282-301), or nothing (CONSTANT).  As
+            // (v >> k) zeros, then `one | (v & m)` in len0 bits: Rice k, 1 << k, (1 << k) - 1, k + 1; raw 32, 0, mask(w), w.
+            uint32_t ka, onea, ma, lena, ja, kb, oneb, mb, lenb, jb;
+#define ZF3_FIELD(U, K, ONE, M, LEN, JS)                                                                   \
+    {                                                                                                      \
+        const bool rice = U.kind == kFixed && !(U.choice & 0x80u);                                         \
+        const uint32_t w = U.kind == kFixed ? (U.choice & 0x7fu) : U.kind == kVerbatim ? U.bps : 0u;       \
+        K = rice ? w : 32u;                                                                                \
+        ONE = rice ? 1u << (w & 31u) : 0u;                                                                 \
+        M = rice ? ONE - 1u : ~shl32(0xffffffffu, w);                                                      \
+        LEN = rice ? w + 1u : w;                                                                           \
+        JS = (t == 0 && U.kind == kFixed) ? U.order : 0u;                                                  \
+    }
+            ZF3_FIELD(ua, ka, onea, ma, lena, ja)
+            ZF3_FIELD(ub, kb, oneb, mb, lenb, jb)
+#undef ZF3_FIELD
+            const bool fast = ua.maxq + lena <= 32u && ub.maxq + lenb <= 32u;  // false for 33-bit samples as well
+            if (__builtin_expect(fast, 1)) {  // every field has at most 32 bits: two independent chains, no branches
+                // Four trips over one piece of code (the arrays rotate by four registers per trip): code size counts as
+                // much as instruction count here
 #pragma unroll 1
                 for (int j0 = 0; j0 < kS; j0 += 4) {
 #pragma unroll
                     for (int jj = 0; jj < 4; jj++) {
                         // the warm-up samples of thread 0 are not coded: an empty field is a no-op
                         const bool oa = (uint32_t)(j0 + jj) >= ja, ob = (uint32_t)(j0 + jj) >= jb;
-                        wa.put(oa ? (onea | (va[jj] & ma)) : 0u, oa ? ((va[jj] >> ka) + lena) : 0u);
-                        wb.put(ob ? (oneb | (vb[jj] & mb)) : 0u, ob ? ((vb[jj] >> kb) + lenb) : 0u);
+                        wa.put(oa ? (onea | (va[jj] & ma)) : 0u, oa ? (shr32(va[jj], ka) + lena) : 0u);
+                        wb.put(ob ? (oneb | (vb[jj] & mb)) : 0u, ob ? (shr32(vb[jj], kb) + lenb) : 0u);
                     }
 #pragma unroll
                     for (int jj = 0; jj < kS - 4; jj++) { va[jj] = va[jj + 4]; vb[jj] = vb[jj + 4]; }
@@ -1395,7 +1414,8 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #pragma unroll
                     for (int j = 0; j < kS; j++) v[j] = ch ? vb[j] : va[j];
                     BitW w = ch ? wb : wa;
-                    sub_body<WIDE>(w, t, ch ? ub : ua, v);
+                    sub_body<WIDE>(w, ch ? ub : ua, v, ch ? kb : ka, ch ? oneb : onea, ch ? mb : ma, ch ? lenb : lena,
+                                   ch ? jb : ja);
                     if (ch) wb = w;
                     else wa = w;
                 }
