@@ -676,34 +676,41 @@ ZF_NOINLINE void lb_start(Smem<BYTES> &sm, const LbArgs job, int lane, const Pen
     lb_issue(sm, job, lane);
 }
 
-// warp 0: take the round that is in flight (waits for it if it has not landed), start the next one if needed
+// one warp: take the round that is in flight (waits for it if it has not landed), start the next one if needed.
+// Lane l examines descriptors hi - 4 l - j, j = 0 (nearest) .. 3, without branches: two 16-byte loads, then the first
+// prefix / unpublished flag of the lane decides which of its values count.
 template <int BYTES>
 ZF_NOINLINE void lb_step(Smem<BYTES> &sm, const LbArgs job, int lane, const Pend P) {
     cp_async_wait_all();
     __syncwarp();
     const int i = sm.lb_i;
+    const unsigned long long excl0 = sm.lb_excl;
     const int hi = i | 1, base = hi - 127;
+    const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(&sm.lbwin[124 - 4 * lane]);
+    const ulonglong2 far2 = wp[0], near2 = wp[1];
+    const unsigned long long dd[4] = {near2.y, near2.x, far2.y, far2.x};  // nearest first
     unsigned long long sum = 0;
-    bool found = false, invalid = false;
+    bool open = true, found = false, invalid = false;  // open: neither a prefix nor a gap met so far
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int idx = hi - 4 * lane - j;  // j = 0 is the nearest one
-        if (!found && !invalid && idx <= i) {
-            const unsigned long long d = idx < 0 ? kFlagPrefix : sm.lbwin[idx - base];
-            const uint32_t flag = (uint32_t)(d >> 62);
-            if (flag == 0u) invalid = true;
-            else {
-                sum += d & kValueMask;
-                found = flag == 2u;
-            }
-        }
+        const int idx = hi - 4 * lane - j;
+        unsigned long long d = dd[j];
+        d = idx < 0 ? kFlagPrefix : d;      // in front of the first frame: prefix 0
+        d = idx > i ? kFlagAggregate : d;   // the pending frame itself (hi = i + 1): nothing
+        const uint32_t flag = (uint32_t)(d >> 62);
+        sum += open ? (d & kValueMask) : 0ull;
+        found = found || (open && flag == 2u);
+        invalid = invalid || (open && flag == 0u);
+        open = open && flag == 1u;
     }
     const uint32_t pmask = __ballot_sync(0xffffffffu, found);
     const uint32_t imask = __ballot_sync(0xffffffffu, invalid);
     const uint32_t first_p = pmask ? ctz32(pmask) : 32u;
     const uint32_t need = first_p >= 31u ? 0xffffffffu : ((2u << first_p) - 1u);
-    const unsigned long long tot = warp_sum(((uint32_t)lane <= first_p) ? sum : 0ull);
-    const unsigned long long excl = sm.lb_excl + tot;
+    // lanes in front of the first prefix lane hold aggregates only (4 frames < 2^32 bytes); the prefix lane's sum is 64-bit
+    const uint32_t agg = reduce_add(((uint32_t)lane < first_p) ? (uint32_t)sum : 0u);
+    const unsigned long long pre = __shfl_sync(0xffffffffu, sum, (int)(first_p & 31u));
+    const unsigned long long excl = excl0 + agg + (first_p < 32u ? pre : 0ull);
     __syncwarp();  // every lane has read the window and the state
     if (imask & need) {  // a predecessor has not published its size yet: fetch the same window again
         lb_issue(sm, job, lane);
