@@ -187,6 +187,14 @@ int zf_encode_wav_memory(const uint8_t *wav, size_t wav_len, uint8_t **flac, siz
                          int n_devices);
 void zf_free(void *p);
 
+/*
+ * Page-locked host memory for PCM / FLAC buffers (the counterpart of the sample buffer wav2flac.zig:72 takes from its
+ * allocator).  zf_encode_pcm copies straight from / into such buffers; any other host memory is staged through the
+ * encoder's own pinned buffers with an extra host copy per batch.  Returns ZF_ERR_NOMEM / ZF_ERR_NO_DEVICE on failure.
+ */
+int zf_host_alloc(size_t bytes, void **out);
+void zf_host_free(void *p);
+
 /* ---- benchmark / test utility --------------------------------------------------------------------------- */
 
 /* Deterministic synthetic stereo PCM: count inter-channel samples starting at stream

@@ -206,6 +206,25 @@ def test_pageable_and_pinned_host_buffers_agree(zf, oracle):
         assert got.tobytes() == ref.tobytes(), per
 
 
+def test_host_alloc_buffers(zf, oracle):
+    # PCM read into, and FLAC returned in, memory from zf_host_alloc: same bytes as through pageable memory
+    n = 50 * 4096 + 99
+    pcm = zf.synth_pcm(n, 48000, 24)
+    enc = zf.Encoder(zf.Config.default(2, 24), 48000, max_frames_per_batch=16)
+    try:
+        ref, ref_sizes = enc.encode_pcm(pcm, n, 0)
+        with zf.HostBuffer(pcm.size) as hin, zf.HostBuffer(enc.max_batch_bytes(51)) as hout:
+            hin.array[:] = pcm
+            got, got_sizes = enc.encode_pcm(hin.array, n, 0, out=hout.array)
+            assert np.array_equal(ref_sizes, got_sizes)
+            assert ref.tobytes() == got.tobytes()
+        cfg = oracle.config(2, 24)
+        o, o_sizes = oracle.encode_pcm(pcm, n, cfg, 48000, 0)
+        assert o.tobytes() == ref.tobytes() and np.array_equal(o_sizes, ref_sizes)
+    finally:
+        enc.close()
+
+
 def test_full_size_config2_properties(zf, oracle):
     """BASELINE config 2 at full size (24-bit / 96 kHz / 600 s: 14 063 frames, 345.6 MB of PCM), checked through
     size-independent properties: the frame sizes add up to the stream, two frame-range shards concatenate to the

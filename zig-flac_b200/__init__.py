@@ -122,6 +122,10 @@ def _lib():
     L.zf_encode_wav_memory.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.c_int]
     L.zf_free.argtypes = [vp]
     L.zf_free.restype = None
+    L.zf_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.zf_host_alloc.restype = C.c_int
+    L.zf_host_free.argtypes = [vp]
+    L.zf_host_free.restype = None
     L.zf_synth_pcm.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]
     _LIB = L
     return L
@@ -360,6 +364,30 @@ def wav_to_flac(wav_bytes, devices=None):
     out = bytes((C.c_uint8 * n.value).from_address(p.value))
     _lib().zf_free(p)
     return ZF_OK, out
+
+
+class HostBuffer:
+    """Page-locked host memory from zf_host_alloc as a numpy uint8 array (`.array`); release with close()."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        rc = _lib().zf_host_alloc(nbytes, C.byref(p))
+        if rc != ZF_OK:
+            raise FlacGpuError(rc, "zf_host_alloc")
+        self._p = p
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(p.value))[:nbytes]
+
+    def close(self):
+        if self._p is not None:
+            self.array = None
+            _lib().zf_host_free(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def encode_file(in_path, out_path, devices=None):

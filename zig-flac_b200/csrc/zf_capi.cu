@@ -592,6 +592,27 @@ void zf_encoder_destroy(zf_encoder *e) {
     delete e;
 }
 
+int zf_host_alloc(size_t bytes, void **out) {
+    if (!out) return ZF_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return ZF_ERR_NO_DEVICE;
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return ZF_ERR_NOMEM;
+    }
+    *out = p;
+    return ZF_OK;
+}
+
+void zf_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 int zf_encode_submit(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channel, uint64_t first_frame_number) {
     if (!e || (!pcm && samples_per_channel)) return ZF_ERR_INVALID_ARG;
     if (e->slot[0].busy) return ZF_ERR_BUSY;
