@@ -1207,10 +1207,11 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             const uint32_t m = (uint32_t)t;
             const uint32_t lvl = m ? floor_log2(m) : 0u;
             const uint32_t j = m - (1u << lvl);
-#pragma unroll 1
+            // every candidate, FIXED or not (what a CONSTANT / VERBATIM candidate yields is never looked at): without the
+            // early exit two candidates' dependent chains interleave
+#pragma unroll 2
             for (uint32_t s = 0; s < 4; s++) {
                 const Dec &d = sm.dec[s];
-                if (d.kind != kFixed) continue;
                 uint32_t choice = 0, cost = 0;
                 unsigned long long S = 0;
                 uint32_t B = 0;
