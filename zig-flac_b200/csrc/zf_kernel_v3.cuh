@@ -1170,9 +1170,10 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 int32_t mn_a = 0, mx_a = 0, mn_b = 0, mx_b = 0;
                 if (fix_a) ZF3_LEAF(slot_a, A, sum_a, mn_a, mx_a)
                 if (fix_b) ZF3_LEAF(slot_b, B, sum_b, mn_b, mx_b)
-#pragma unroll 1
-                for (uint32_t h = 0; h < 2; h++) {  // one copy of: width, leaf parameter, tree levels 7..3
-                    if (!(h ? fix_b : fix_a)) continue;
+                // width, leaf parameter, tree levels 7..3 of both candidates (FIXED or not: what the others yield is never
+                // looked at), interleaved: the chains are long and dependent
+#pragma unroll
+                for (uint32_t h = 0; h < 2; h++) {
                     const uint32_t slot = h ? slot_b : slot_a;
                     const uint32_t order = sm.dec[slot].order, waste = sm.dec[slot].waste, P = sm.dec[slot].P;
                     const uint32_t jstart = (t == 0) ? order : 0u;
