@@ -1461,10 +1461,12 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #pragma unroll 1
                         for (int k = 1; k <= kCrcChunkWords / 4; k++) {
                             const uint4 nx = p[k];  // next four words meanwhile (the last trip reads into the padding)
-                            a = q_fold((a << 4) ^ (a << 2) ^ v.x);
-                            a = q_fold((a << 4) ^ (a << 2) ^ v.y);
-                            a = q_fold((a << 4) ^ (a << 2) ^ v.z);
-                            a = q_fold((a << 4) ^ (a << 2) ^ v.w);
+                            // two words per dependent step: a x^64 + w0 x^32 + w1 with x^64 = x^8 + x^4 and
+                            // x^32 = x^4 + x^2 (mod Q); the w0 term does not depend on a
+                            const uint32_t f0 = q_fold(v.x), f2 = q_fold(v.z);
+                            const uint32_t u0 = (f0 << 4) ^ (f0 << 2) ^ v.y, u2 = (f2 << 4) ^ (f2 << 2) ^ v.w;
+                            a = q_fold((a << 8) ^ (a << 4) ^ u0);
+                            a = q_fold((a << 8) ^ (a << 4) ^ u2);
                             par ^= v.x ^ v.y ^ v.z ^ v.w;
                             v = nx;
                         }
