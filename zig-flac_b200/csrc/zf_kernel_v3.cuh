@@ -1430,17 +1430,17 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 }
             }
         }
+        // frame header, one byte per lane of the last warp: worked out in front of the barrier (between the two barriers
+        // the other seven warps would only wait for it), ORed in behind it
+        uint32_t hbyte = 0, hlen = 0;
+        if (fits && warp == kW - 1) hbyte = header_byte(sm.crc8tab, lane, frame_number, depth, ch_type, rate_code_v, hlen);
         __syncthreads();  // all complete words stored
         if (fits) {
             wa.or_tail();
             wb.or_tail();
-            if (warp == kW - 1) {  // frame header, one byte per lane
-                uint32_t hlen;
-                const uint32_t byte = header_byte(sm.crc8tab, lane, frame_number, depth, ch_type, rate_code_v, hlen);
-                if ((uint32_t)lane < hlen) {
-                    const uint32_t b = lead + (uint32_t)lane;
-                    atomicOr(&sm.bits[b >> 2], byte << (24u - 8u * (b & 3u)));
-                }
+            if ((uint32_t)lane < hlen) {  // hlen = 0 in the other warps
+                const uint32_t b = lead + (uint32_t)lane;
+                atomicOr(&sm.bits[b >> 2], hbyte << (24u - 8u * (b & 3u)));
             }
         }
         __syncthreads();
