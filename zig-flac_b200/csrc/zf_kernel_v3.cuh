@@ -12,11 +12,16 @@
 //   * decisions that every thread needs (partition order, method, FIXED vs VERBATIM, stereo mode) are computed
 //     redundantly by every warp from shared per-level partial sums: no decision barrier, no broadcast
 //   * bit writer: right-aligned 64-bit shift register; a word is stored (plain, predicated) by the one thread whose
-//     bit range crosses the word's end, partial tail words are ORed in after a barrier; the two subframes are
-//     written as two interleaved dependency chains
+//     bit range crosses the word's end, partial tail words are ORed in after a barrier, so the buffer is never
+//     cleared (only the header words and a partial last word are); the two subframes are written as two interleaved
+//     dependency chains, and every kind of field (Rice code, escaped or VERBATIM raw bits) goes through the same
+//     branch-free loop -- a raw field is a Rice code with k = 32
 //   * the stream is placed in the bit buffer so that it ENDS on a 16-byte boundary (leading zero bytes do not change
 //     a CRC with zero init), CRC-16 is computed table-free in GF(2)[x]/(x^15+x+1) x parity
-//     (x^16+x^15+x^2+1 = (x+1)(x^15+x+1)): Horner step  a <- a*(x^4+x^2) + word,  x^32 = x^4+x^2 (mod x^15+x+1)
+//     (x^16+x^15+x^2+1 = (x+1)(x^15+x+1)): Horner step  a <- a*(x^4+x^2) + word,  x^32 = x^4+x^2 (mod x^15+x+1),
+//     two words per dependent step; chunks are combined by a carry-less multiply done with integer multiplies
+//   * long dependent chains (parameter search, shuffle tree) run two candidates at a time; FIXED or not, every
+//     candidate is evaluated -- no early exits inside a warp
 //   * deferred epilogue: a finished frame stays in the bit buffer while the next one is analysed; its output offset
 //     comes from a decoupled look-back whose descriptor window is fetched with cp.async (no registers, no waiting),
 //     and it is copied out (16-byte stores) just before the bit buffer is needed again
