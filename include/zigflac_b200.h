@@ -94,7 +94,8 @@ int zf_encode_pcm(zf_encoder *enc, const uint8_t *pcm, uint64_t samples_per_chan
 
 /* Asynchronous pair for pipelining (one batch in flight per handle): submit copies the input to the
  * device and launches the kernels on the handle's stream; collect waits and copies results back.
- * `pcm` must stay valid until submit returns; `out`/`frame_sizes` are only touched by collect. */
+ * `pcm` must stay valid until submit returns (pageable memory is staged at once; for page-locked memory
+ * submit waits for the upload, not for the kernels); `out`/`frame_sizes` are only touched by collect. */
 int zf_encode_submit(zf_encoder *enc, const uint8_t *pcm, uint64_t samples_per_channel, uint64_t first_frame_number);
 int zf_encode_collect(zf_encoder *enc, uint8_t *out, size_t out_cap, size_t *out_len, uint32_t *frame_sizes,
                       uint32_t frame_sizes_cap, uint32_t *n_frames);
@@ -107,6 +108,16 @@ int zf_encode_collect(zf_encoder *enc, uint8_t *out, size_t out_cap, size_t *out
  */
 int zf_encode_device(zf_encoder *enc, const void *d_pcm, uint64_t samples_per_channel, uint64_t first_frame_number,
                      void *d_out, size_t out_cap, uint32_t *d_frame_sizes, uint64_t *d_total_bytes, void *stream);
+/*
+ * Device-resident batches of one handle share the handle's control block (frame tickets, look-back descriptors,
+ * status word): consecutive calls are ordered on the device by the library even when they name different streams,
+ * and ZF_ERR_BUSY is returned while a zf_encode_submit batch has not been collected.  Frames that do not fit
+ * out_cap are not written, but *d_total_bytes still counts them: total > out_cap means overflow.  This call reports
+ * the same from the status word of the most recent device-resident batch (waits for that batch).
+ */
+#define ZF_STATUS_OUT_OVERFLOW 1u /* out_cap exceeded: Writer.Error.WriteFailed */
+#define ZF_STATUS_INTERNAL 2u     /* a frame exceeded maxFrameBytes (cannot happen for valid configurations) */
+int zf_encode_device_status(zf_encoder *enc, uint32_t *flags);
 
 /* Encoder.writeFrame itself (encoder.zig:234): ONE frame from planar, sign-extended int32 planes
  * (the layout of Encoder.samples the caller fills through WavReader.fillSamples, wav_reader.zig:44).

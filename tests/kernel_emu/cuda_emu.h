@@ -125,6 +125,9 @@ static inline void fence_proxy_async() {}
 static inline void mbar_expect_tx(unsigned long long *, uint32_t) {}
 static inline void mbar_wait(unsigned long long *, uint32_t) {}
 static inline void tma_load_1d(void *dst, const void *src, uint32_t bytes, unsigned long long *) { memcpy(dst, src, bytes); }
+static inline void tma_load_1d_elect(void *dst, const void *src, uint32_t bytes, unsigned long long *) {
+    if (((int)emu::g_threadIdx.x & 31) == 0) memcpy(dst, src, bytes);
+}
 static inline void cp_async16_cg(void *dst, const void *src) { memcpy(dst, src, 16); }
 static inline void cp_async_commit() {}
 static inline void pdl_launch_dependents() {}

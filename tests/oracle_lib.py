@@ -68,6 +68,7 @@ def build(force=False):
     """Compile the oracle with its committed Makefile (outputs only into oracle/_ref/)."""
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("zigflac_oracle.c", "flac_decode.c", "zigflac_oracle.h",
                                                   "oracle_cli.c", "Makefile")]
+    srcs.append(os.path.join(ROOT, "zig-flac_b200", "csrc", "zf_synth.c"))
     stale = force or not os.path.exists(ORACLE_SO) or any(
         os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs)
     if stale:
@@ -117,6 +118,28 @@ def lib():
     L.fd_free.argtypes = [C.c_void_p]
     _lib = L
     return L
+
+
+_synth = None
+
+
+def synth_pcm(samples, sample_rate, bit_depth, first_sample=0, seed=0x5EED, threads=None):
+    """The benchmark's synthetic stereo PCM from oracle/_ref/libzf_synth.so -- the same generator source as
+    the product's zf_synth_pcm, built on its own so that the reference arm of bench.py loads no product code."""
+    global _synth
+    if _synth is None:
+        build()
+        so = os.path.join(ORACLE_DIR, "_ref", "libzf_synth.so")
+        if not os.path.exists(so):
+            subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+        _synth = C.CDLL(so)
+        _synth.zf_synth_pcm.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]
+    out = np.empty(samples * 2 * (bit_depth // 8), dtype=np.uint8)
+    rc = _synth.zf_synth_pcm(out.ctypes.data, first_sample, samples, sample_rate, bit_depth, seed,
+                             threads or (os.cpu_count() or 1))
+    if rc != 0:
+        raise ValueError("synth_pcm: unsupported format")
+    return out
 
 
 def _buf(b):

@@ -8,6 +8,8 @@ import re
 import numpy as np
 import pytest
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_library_exports_every_declared_symbol(zf):
     header = open(zf.HEADER_PATH).read()
@@ -18,6 +20,29 @@ def test_library_exports_every_declared_symbol(zf):
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
     assert lib.zf_abi_version() == 1
+
+
+def test_static_library_carries_the_same_abi(zf, tmp_path):
+    """libzigflac_b200.a (BASELINE north_star: "nvcc-built sm_100a static library, linked from build.zig") defines every
+    declared symbol, keeps the oracle out, and links into a program with nothing but the toolkit's static cudart --
+    the link line INTEGRATION.md gives for build.zig."""
+    import subprocess
+    static = os.path.join(os.path.dirname(zf.LIB_PATH), "libzigflac_b200.a")
+    assert os.path.exists(static), "run python zig-flac_b200/build.py"
+    header = re.sub(r"/\*.*?\*/", "", open(zf.HEADER_PATH).read(), flags=re.S)
+    names = set(re.findall(r"\b(zf_[a-z0-9_]+)\s*\(", header))
+    syms = subprocess.run(["nm", "--defined-only", static], capture_output=True, text=True).stdout
+    defined = set(re.findall(r" T (zf_[a-z0-9_]+)", syms))
+    assert not (names - defined), sorted(names - defined)
+    assert " zo_" not in syms and "fd_decode" not in syms
+    spec_path = os.path.join(os.path.dirname(zf.LIB_PATH), "build.py")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_zf_build_t", spec_path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    exe = mod.link_static_check(str(tmp_path / "flac_static"))
+    r = subprocess.run([exe], capture_output=True)
+    assert r.returncode == 1 and b"usage: flac in_file.wav out_file.flac" in r.stderr  # cli.zig:17-20
 
 
 def test_no_cpu_fallback(zf):
@@ -111,3 +136,30 @@ def test_synth_generator_properties(zf):
     s = v[:, 0] | (v[:, 1] << 8) | (v[:, 2] << 16)
     s = np.where(s >= 1 << 23, s - (1 << 24), s)
     assert np.abs(s).max() < 0.75 * (1 << 23) and np.abs(s).max() > 1000  # no clipping, not silent
+
+
+def test_reference_arm_maps_no_product_library():
+    """bench.py --impl reference times the oracle only: the product .so must not even be mapped into that process, and
+    its `config` is the product arm's `config` (the driver compares the two lines)."""
+    import json
+    import subprocess
+    import sys
+    code = (
+        "import runpy, sys\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '2', '--warmup', '1', '--workload', 'c1_16bit_44k1_60s']\n"
+        "try:\n"
+        "    runpy.run_path('bench.py', run_name='__main__')\n"
+        "except SystemExit:\n"
+        "    pass\n"
+        "print('MAPS', sorted({l.split()[-1] for l in open('/proc/self/maps') if '.so' in l and ('zig' in l or 'zf_' in l)}))\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, check=True)
+    lines = r.stdout.strip().splitlines()
+    maps = [l for l in lines if l.startswith("MAPS")][0]
+    assert "libzigflac_b200" not in maps and "libzigflac_oracle.so" in maps, maps
+    line = json.loads([l for l in lines if l.startswith("{")][0])
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.make_config("c1_16bit_44k1_60s", 1)
+    assert line["config"]["l2_resident"] is True

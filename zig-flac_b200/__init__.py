@@ -27,6 +27,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "zigflac_b200.h")
 ZF_OK = 0
 ZF_ERR_NO_DEVICE = -3
 ZF_ERR_OUT_TOO_SMALL = -6
+ZF_ERR_BUSY = -7
 
 
 class FlacGpuError(RuntimeError):
@@ -98,6 +99,7 @@ def _lib():
     L.zf_encode_submit.argtypes = [vp, vp, C.c_uint64, C.c_uint64]
     L.zf_encode_collect.argtypes = [vp, vp, C.c_size_t, C.POINTER(C.c_size_t), vp, C.c_uint32, C.POINTER(C.c_uint32)]
     L.zf_encode_device.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp, C.c_size_t, vp, vp, vp]
+    L.zf_encode_device_status.argtypes = [vp, C.POINTER(C.c_uint32)]
     L.zf_write_frame.argtypes = [vp, C.POINTER(vp), C.c_uint32, C.c_uint64, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.zf_last_batch_stats.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     L.zf_kernel_times.argtypes = [vp, C.POINTER(C.c_float), C.c_uint32, C.POINTER(C.c_uint32)]
@@ -331,6 +333,37 @@ class Encoder:
                                      out_cap, d_sizes_ptr, d_total_ptr, stream_ptr)
         if rc != ZF_OK:
             raise FlacGpuError(rc, "encode_device")
+
+    def device_status(self):
+        """Status flags of the most recent encode_device batch (waits for it)."""
+        f = C.c_uint32()
+        rc = _lib().zf_encode_device_status(self.handle, C.byref(f))
+        if rc != ZF_OK:
+            raise FlacGpuError(rc, "encode_device_status")
+        return f.value
+
+    def submit(self, pcm, samples_per_channel, first_frame_number=0):
+        """zf_encode_submit: upload + kernels of one batch, asynchronous; `pcm` may be reused on return."""
+        pcm = _u8(pcm)
+        rc = _lib().zf_encode_submit(self.handle, pcm.ctypes.data, samples_per_channel, first_frame_number)
+        if rc != ZF_OK:
+            raise FlacGpuError(rc, "encode_submit")
+        self._submitted = samples_per_channel
+
+    def collect(self, out=None):
+        """zf_encode_collect: wait for the submitted batch -> (frame bytes, frame sizes)."""
+        bs = self.config.block_size
+        frames = (self._submitted + bs - 1) // bs
+        if out is None:
+            out = np.empty(self.max_batch_bytes(frames), dtype=np.uint8)
+        sizes = np.zeros(max(frames, 1), dtype=np.uint32)
+        ln = C.c_size_t()
+        nf = C.c_uint32()
+        rc = _lib().zf_encode_collect(self.handle, out.ctypes.data, out.size, C.byref(ln), sizes.ctypes.data, sizes.size,
+                                      C.byref(nf))
+        if rc != ZF_OK:
+            raise FlacGpuError(rc, "encode_collect")
+        return out[:ln.value], sizes[:nf.value]
 
     def last_batch_stats(self):
         ms = C.c_float()

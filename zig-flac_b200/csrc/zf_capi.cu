@@ -79,6 +79,8 @@ struct zf_encoder {
     uint16_t *d_pow8 = nullptr;
     Slot slot[kSlots];  // submit/collect use slot 0 only; zf_encode_pcm rotates through all of them
     cudaStream_t s_up = nullptr, s_down = nullptr;  // all uploads / all downloads, each in batch order on its own stream
+    cudaEvent_t ev_dev = nullptr;  // end of the last zf_encode_device batch: it shares slot 0's control block and descriptors
+    bool dev_pending = false;
     size_t frame_pcm_bytes = 0;
     size_t max_frame_bytes = 0;
     bool stereo = false;
@@ -404,6 +406,10 @@ int slot_submit(zf_encoder *e, Slot &sl, const uint8_t *pcm, uint64_t samples, u
     ZF_CUDA(cudaEventRecord(sl.ev_up, e->s_up));
     tr_mark(e, e->s_up, kTrUp1);
     ZF_CUDA(cudaStreamWaitEvent(sl.stream, sl.ev_up, 0));
+    if (&sl == &e->slot[0] && e->dev_pending) {  // a zf_encode_device batch may still be using this slot's control block
+        ZF_CUDA(cudaStreamWaitEvent(sl.stream, e->ev_dev, 0));
+        e->dev_pending = false;
+    }
     ZF_CUDA(cudaEventRecord(sl.ev_start, sl.stream));
     int launches = 0;
     rc = launch_batch(e, sl, sl.d_pcm, samples, first_frame_number, sl.d_out, sl.out_cap, sl.d_sizes, sl.d_total, sl.stream,
@@ -555,7 +561,8 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     rc = setup_kernels(e);
     for (int i = 0; i < kSlots && !rc; i++) rc = slot_init(e, e->slot[i]);
     if (!rc && (cudaStreamCreateWithFlags(&e->s_up, cudaStreamNonBlocking) != cudaSuccess ||
-                cudaStreamCreateWithFlags(&e->s_down, cudaStreamNonBlocking) != cudaSuccess))
+                cudaStreamCreateWithFlags(&e->s_down, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&e->ev_dev, cudaEventDisableTiming) != cudaSuccess))
         rc = ZF_ERR_CUDA;
     if (!rc) {
         std::vector<uint16_t> pw(kPow8Len);
@@ -587,6 +594,7 @@ void zf_encoder_destroy(zf_encoder *e) {
     for (int i = 0; i < kSlots; i++) slot_free(e->slot[i]);
     if (e->s_up) cudaStreamDestroy(e->s_up);
     if (e->s_down) cudaStreamDestroy(e->s_down);
+    if (e->ev_dev) cudaEventDestroy(e->ev_dev);
     cudaFree(e->d_pow8);
     for (cudaEvent_t ev : e->tr_ev) cudaEventDestroy(ev);
     delete e;
@@ -615,9 +623,15 @@ void zf_host_free(void *p) {
 
 int zf_encode_submit(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channel, uint64_t first_frame_number) {
     if (!e || (!pcm && samples_per_channel)) return ZF_ERR_INVALID_ARG;
-    if (e->slot[0].busy) return ZF_ERR_BUSY;
+    if (e->slot[0].busy || e->slot[0].draining) return ZF_ERR_BUSY;
     ZF_CUDA(cudaSetDevice(e->cfg.device_id));
-    return slot_submit(e, e->slot[0], pcm, samples_per_channel, first_frame_number);
+    int rc = slot_submit(e, e->slot[0], pcm, samples_per_channel, first_frame_number);
+    if (rc) return rc;
+    // The header's contract: `pcm` may be reused as soon as submit returns.  Pageable memory has been copied to the pinned
+    // staging buffer already; pinned / managed memory is read by the copy engine itself, so wait for that upload (only
+    // the upload: the kernels and the download stay asynchronous).
+    if (samples_per_channel && is_pinned_or_device_visible(pcm)) ZF_CUDA(cudaEventSynchronize(e->slot[0].ev_up));
+    return ZF_OK;
 }
 
 int zf_encode_collect(zf_encoder *e, uint8_t *out, size_t out_cap, size_t *out_len, uint32_t *frame_sizes,
@@ -730,14 +744,33 @@ int zf_encode_device(zf_encoder *e, const void *d_pcm, uint64_t samples_per_chan
     if (!e || !d_out || !d_frame_sizes || !d_total_bytes || (!d_pcm && samples_per_channel)) return ZF_ERR_INVALID_ARG;
     ZF_CUDA(cudaSetDevice(e->cfg.device_id));
     Slot &sl = e->slot[0];
+    // the batch uses slot 0's tickets, status word, look-back descriptors and last-frame scratch
+    if (sl.busy || sl.draining) return ZF_ERR_BUSY;
     cudaStream_t s = stream ? (cudaStream_t)stream : sl.stream;
+    // ... and so did the previous device-resident batch, which may have been enqueued on another stream: order them
+    if (e->dev_pending) ZF_CUDA(cudaStreamWaitEvent(s, e->ev_dev, 0));
     ZF_CUDA(cudaEventRecord(sl.ev_start, s));
     int launches = 0;
     int rc = launch_batch(e, sl, (const uint8_t *)d_pcm, samples_per_channel, first_frame_number, (uint8_t *)d_out, out_cap,
                           d_frame_sizes, (unsigned long long *)d_total_bytes, s, &launches);
     if (rc) return rc;
     ZF_CUDA(cudaEventRecord(sl.ev_stop, s));
+    ZF_CUDA(cudaEventRecord(e->ev_dev, s));
+    e->dev_pending = true;
     e->launches_last = launches;
+    return ZF_OK;
+}
+
+int zf_encode_device_status(zf_encoder *e, uint32_t *flags) {
+    if (!e || !flags) return ZF_ERR_INVALID_ARG;
+    ZF_CUDA(cudaSetDevice(e->cfg.device_id));
+    if (e->dev_pending) {
+        ZF_CUDA(cudaEventSynchronize(e->ev_dev));
+        e->dev_pending = false;
+    }
+    unsigned int st = 0;
+    ZF_CUDA(cudaMemcpy(&st, e->slot[0].d_ctl + 2, sizeof st, cudaMemcpyDeviceToHost));
+    *flags = (st & zf::kStatusOutOverflow ? ZF_STATUS_OUT_OVERFLOW : 0u) | (st & zf::kStatusBitOverflow ? ZF_STATUS_INTERNAL : 0u);
     return ZF_OK;
 }
 

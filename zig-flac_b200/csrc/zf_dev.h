@@ -54,6 +54,20 @@ ZF_DEVICE void tma_load_1d(void *smem_dst, const void *gmem_src, uint32_t bytes,
                  : "memory");
 }
 
+// The same issued by one elected lane of a converged warp (all 32 lanes call it with the same arguments): the addresses
+// stay in uniform registers, so a loop of such copies costs a few uniform-datapath instructions per copy instead of a
+// per-lane serialisation loop.
+ZF_DEVICE void tma_load_1d_elect(void *smem_dst, const void *gmem_src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+        "}\n" ::"r"(smem_addr(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_addr(bar))
+        : "memory");
+}
+
 // ---- Ampere-style asynchronous copy, L2 only (.cg): used to fetch look-back descriptors without holding registers
 ZF_DEVICE void cp_async16_cg(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smem_dst)), "l"(gmem_src) : "memory");

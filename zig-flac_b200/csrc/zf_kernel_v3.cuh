@@ -45,7 +45,29 @@ constexpr int kH = 4;            // history samples in front of a thread's windo
 constexpr int kXn = kS + kH;
 constexpr int kN = 4096;
 constexpr int kW = kT / 32;
-constexpr int kPadWords = 8;     // 32 zero bytes in front of the PCM: history of thread 0
+
+// Raw PCM in shared memory.  Thread t reads "its" row (its sixteen inter-channel samples: 64 / 96 / 128 bytes) with
+// 16-byte loads, and so do its neighbours at the same moment: rows that simply follow one another would put the eight
+// threads of a quarter-warp into 4 / 2 / 1 of the eight 16-byte bank groups (an 8-way conflict on every LDS.128 of
+// 32-bit PCM).  So the frame is laid down in groups of 2 / 4 / 1 rows (128 / 384 / 128 bytes) with 16 bytes of padding
+// behind every group -- one 1-D bulk copy per group -- which sends any eight consecutive rows to eight different bank
+// groups: (4 r + r/2), (6 r + r/4), (9 r) mod 8 are bijections of r mod 8.  A zeroed group in front is "row -1", the
+// history of thread 0.
+template <int BYTES>
+struct Lay {
+    static constexpr int kRowW = 8 * BYTES;  // words per row
+    static constexpr int kGroupRows = BYTES == 4 ? 1 : BYTES == 3 ? 4 : 2;
+    static constexpr int kGroupW = kRowW * kGroupRows;
+    static constexpr int kPitchW = kGroupW + 4;
+    static constexpr int kGroups = kT / kGroupRows;
+    static constexpr int kFrontW = kPitchW;
+    static constexpr int kWords = kFrontW + kGroups * kPitchW;
+    // word offset of row r >= -1 in raw[]
+    static ZF_DEVICE int row(int r) {
+        const int q = r + kGroupRows;
+        return (q / kGroupRows) * kPitchW + (q % kGroupRows) * kRowW;
+    }
+};
 constexpr int kCrcChunkWords = 16;
 // resident CTAs per SM: 16/24-bit: 80 registers, ~66 KB of shared memory each; 32-bit (64-bit chains): 128 registers, ~87 KB
 #ifndef ZF_V3_CTAS16
@@ -73,7 +95,7 @@ struct Scratch {
 
 template <int BYTES>
 struct Smem {
-    alignas(16) uint32_t raw[kPadWords + kN * 2 * BYTES / 4];
+    alignas(16) uint32_t raw[Lay<BYTES>::kWords];
     alignas(16) uint32_t bits[BitBufWords<BYTES>::value + 8];
     alignas(16) uint32_t lvlcost[4][9][16];  // per candidate, per partition order: up to 16 partial cost sums
     alignas(16) uint8_t lvlfive[4][9][16];   // ... and whether a parameter > 14 occurs (5-bit method, rice.zig:383-387)
@@ -120,21 +142,22 @@ ZF_DEVICE uint32_t shr32(uint32_t v, uint32_t s) {
 // WHICH: 0 both channels, 1 left only, 2 right only (the other array is left untouched)
 template <int BYTES, int WHICH>
 ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (&R)[kXn]) {
+    const uint32_t *cur = raw + Lay<BYTES>::row(t), *prev = raw + Lay<BYTES>::row(t - 1);
     if (BYTES == 4) {
-        // two words per inter-channel sample
-        const uint4 *p = reinterpret_cast<const uint4 *>(raw + kPadWords + 2 * (kS * t - kH));
+        // two words per inter-channel sample; history = the last 32 bytes of the row in front
+        const uint4 *pp = reinterpret_cast<const uint4 *>(prev + 24), *pc = reinterpret_cast<const uint4 *>(cur);
 #pragma unroll
         for (int k = 0; k < kXn / 2; k++) {
-            const uint4 v = p[k];
+            const uint4 v = k < 2 ? pp[k] : pc[k - 2];
             if (WHICH != 2) { L[2 * k] = (int32_t)v.x; L[2 * k + 1] = (int32_t)v.z; }
             if (WHICH != 1) { R[2 * k] = (int32_t)v.y; R[2 * k + 1] = (int32_t)v.w; }
         }
     } else if (BYTES == 2) {
-        // one word per inter-channel sample; the window starts 4 samples before 16 t
-        const uint4 *p = reinterpret_cast<const uint4 *>(raw + kPadWords + kS * t - kH);
+        // one word per inter-channel sample; history = the last 16 bytes of the row in front
+        const uint4 *pp = reinterpret_cast<const uint4 *>(prev + 12), *pc = reinterpret_cast<const uint4 *>(cur);
 #pragma unroll
         for (int k = 0; k < kXn / 4; k++) {
-            const uint4 v = p[k];
+            const uint4 v = k < 1 ? pp[0] : pc[k - 1];
             const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
@@ -143,13 +166,13 @@ ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (
             }
         }
     } else {
-        // 6 bytes per inter-channel sample; 128 bytes from byte 96 t - 32 of the PCM (16-byte aligned), the window
-        // (4 history + 16 own samples = 120 bytes) starts 8 bytes in
-        const uint4 *p = reinterpret_cast<const uint4 *>(raw + kPadWords + 24 * t - 8);
+        // 6 bytes per inter-channel sample; the last 32 bytes of the row in front, then the row: the window (4 history +
+        // 16 own samples = 120 bytes) starts 8 bytes in
+        const uint4 *pp = reinterpret_cast<const uint4 *>(prev + 16), *pc = reinterpret_cast<const uint4 *>(cur);
         uint32_t w[32];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            const uint4 v = p[k];
+            const uint4 v = k < 2 ? pp[k] : pc[k - 2];
             w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
         }
 #pragma unroll
@@ -199,16 +222,20 @@ ZF_DEVICE void load_x(const uint32_t *raw, int t, uint32_t slot, long long (&x)[
     }
 }
 
-// four consecutive inter-channel samples starting at sample index i0 (may be -4: the zero pad) of the frame in `raw`
+// inter-channel samples 4 g .. 4 g + 3 of thread t's row, g = 0..3; g = -1: the last four of the row in front (the
+// history; the zeroed front group for thread 0).  16-byte loads only (conflict-free with the padded layout); the
+// 24-byte groups of 24-bit PCM are taken out of two aligned chunks.
 template <int BYTES>
-ZF_DEVICE void load4(const uint32_t *raw, int i0, int32_t (&L)[4], int32_t (&R)[4]) {
+ZF_DEVICE void load4(const uint32_t *raw, int t, int g, int32_t (&L)[4], int32_t (&R)[4]) {
+    const uint32_t *row = raw + (g < 0 ? Lay<BYTES>::row(t - 1) : Lay<BYTES>::row(t));
+    const int gg = g < 0 ? 3 : g;
     if (BYTES == 4) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(raw + kPadWords + 2 * i0);
+        const uint4 *p = reinterpret_cast<const uint4 *>(row + 8 * gg);
         const uint4 v0 = p[0], v1 = p[1];
         L[0] = (int32_t)v0.x; R[0] = (int32_t)v0.y; L[1] = (int32_t)v0.z; R[1] = (int32_t)v0.w;
         L[2] = (int32_t)v1.x; R[2] = (int32_t)v1.y; L[3] = (int32_t)v1.z; R[3] = (int32_t)v1.w;
     } else if (BYTES == 2) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(raw + kPadWords + i0);
+        const uint4 v = *reinterpret_cast<const uint4 *>(row + 4 * gg);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -216,9 +243,12 @@ ZF_DEVICE void load4(const uint32_t *raw, int i0, int32_t (&L)[4], int32_t (&R)[
             R[q] = (int32_t)prmt(w[q], 0, 0xBB32);
         }
     } else {
-        const uint2 *p = reinterpret_cast<const uint2 *>(raw + kPadWords + (i0 * 6) / 4);  // 24 bytes, 8-byte aligned
-        const uint2 v0 = p[0], v1 = p[1], v2 = p[2];
-        const uint32_t w[6] = {v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+        // bytes 24 g .. 24 g + 23 of the row: chunks (3 g) >> 1 and the next one, from their start (g even) or 8 bytes in
+        const uint4 *p = reinterpret_cast<const uint4 *>(row + 4 * ((3 * gg) >> 1));
+        const uint4 v0 = p[0], v1 = p[1];
+        const bool odd = (gg & 1) != 0;
+        const uint32_t w[6] = {odd ? v0.z : v0.x, odd ? v0.w : v0.y, odd ? v1.x : v0.z,
+                               odd ? v1.y : v0.w, odd ? v1.z : v1.x, odd ? v1.w : v1.y};
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const uint32_t a = w[3 * k], b = w[3 * k + 1], d = w[3 * k + 2];
@@ -811,6 +841,22 @@ ZF_DEVICE uint32_t header_byte(const uint8_t *crc8tab, int lane, unsigned long l
     return b;
 }
 
+// All warps (converged): warp w brings in rows 32 w .. 32 w + 31 of a frame, one bulk copy per group of the padded layout,
+// issued by an elected lane from uniform registers.  Thread 0 arms the barrier with the frame's byte count (a copy that
+// completes first only drives the transaction count negative for a moment; the phase cannot end before that arrival).
+template <int BYTES>
+ZF_DEVICE void fetch_frame(Smem<BYTES> &sm, const uint8_t *frame_pcm, int warp) {
+    typedef Lay<BYTES> LY;
+    constexpr int kPer = 32 / LY::kGroupRows;
+    const int wu = __shfl_sync(0xffffffffu, warp, 0);
+    fence_proxy_async();  // the reads of the frame that is being replaced were generic-proxy accesses
+    uint32_t *dst = sm.raw + LY::kFrontW + wu * (kPer * LY::kPitchW);
+    const uint8_t *src = frame_pcm + (size_t)wu * (size_t)(kPer * LY::kGroupW * 4);
+#pragma unroll 4
+    for (int k = 0; k < kPer; k++)
+        tma_load_1d_elect(dst + k * LY::kPitchW, src + (size_t)k * (size_t)(LY::kGroupW * 4), (uint32_t)LY::kGroupW * 4u, &sm.mbar);
+}
+
 template <int BYTES>
 __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_v3_kernel(const FrameJob job) {
     extern __shared__ __align__(16) unsigned char zf_smem[];
@@ -829,7 +875,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #pragma unroll
         for (int k = 0; k < 8; k++) v8 = (v8 & 0x80u) ? ((v8 << 1) ^ 0x07u) : (v8 << 1);
         sm.crc8tab[t] = (uint8_t)v8;
-        if (t < kPadWords) sm.raw[t] = 0;
+        if (t < Lay<BYTES>::kFrontW) sm.raw[t] = 0;  // "row -1": the history of thread 0
         uint4 *bz = reinterpret_cast<uint4 *>(sm.bits);
         const uint4 z = {0, 0, 0, 0};
         for (int k = t; k < (BitBufWords<BYTES>::value + 8) / 4; k += kT) bz[k] = z;
@@ -842,17 +888,16 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 mbar_init(&sm.mbar, 1);
                 fence_mbar_init();
             }
-            const uint32_t f = atomicAdd(job.ticket, 1u);
-            sm.next_frame = f;
-            if (tma && f < job.n_frames) {
-                mbar_expect_tx(&sm.mbar, frame_bytes);
-                tma_load_1d(sm.raw + kPadWords, job.pcm + (size_t)f * job.frame_stride, frame_bytes, &sm.mbar);
-            }
+            sm.next_frame = atomicAdd(job.ticket, 1u);
         }
     }
     __syncthreads();
     uint32_t phase = 0;
-    uint32_t f = sm.next_frame;
+    uint32_t f = __shfl_sync(0xffffffffu, sm.next_frame, 0);
+    if (tma && f < job.n_frames) {
+        if (t == 0) mbar_expect_tx(&sm.mbar, frame_bytes);
+        fetch_frame<BYTES>(sm, job.pcm + (size_t)f * job.frame_stride, warp);
+    }
     uint32_t rate_extra;
     const uint32_t rate_code_v = rate_code(job.sample_rate, rate_extra);  // a table rate: no trailer (checked on the host)
     LbArgs lba;
@@ -868,13 +913,16 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             mbar_wait(&sm.mbar, phase);
             phase ^= 1u;
         } else {
+            // source not 16-byte aligned (a caller's device pointer): plain loads into the same padded layout
             const uint8_t *src = job.pcm + (size_t)f * job.frame_stride;
-            uint8_t *dst = reinterpret_cast<uint8_t *>(sm.raw + kPadWords);
+            constexpr uint32_t kRowW = (uint32_t)Lay<BYTES>::kRowW;
             if ((((uintptr_t)src) & 3u) == 0) {
                 const uint32_t *s32 = reinterpret_cast<const uint32_t *>(src);
-                for (uint32_t k = t; k < frame_bytes / 4u; k += kT) sm.raw[kPadWords + k] = s32[k];
+                for (uint32_t k = t; k < frame_bytes / 4u; k += kT) sm.raw[Lay<BYTES>::row((int)(k / kRowW)) + k % kRowW] = s32[k];
             } else {
-                for (uint32_t k = t; k < frame_bytes; k += kT) dst[k] = src[k];
+                uint8_t *dst = reinterpret_cast<uint8_t *>(sm.raw);
+                for (uint32_t k = t; k < frame_bytes; k += kT)
+                    dst[4u * (uint32_t)Lay<BYTES>::row((int)(k / (4u * kRowW))) + k % (4u * kRowW)] = src[k];
             }
             __syncthreads();
         }
@@ -891,7 +939,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 ca.init(); cb.init();
                 {
                     int32_t L[4], R[4];
-                    load4<BYTES>(sm.raw, kS * t - kH, L, R);
+                    load4<BYTES>(sm.raw, t, -1, L, R);
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const long long l = L[q], r = R[q];
@@ -903,7 +951,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #pragma unroll 1
                 for (int g = 0; g < kS / 4; g++) {
                     int32_t L[4], R[4];
-                    load4<BYTES>(sm.raw, kS * t + 4 * g, L, R);
+                    load4<BYTES>(sm.raw, t, g, L, R);
                     long long xa[4], xb[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
@@ -954,7 +1002,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             c0.init(); c1.init(); c2.init(); c3.init();
             {
                 int32_t L[4], R[4];
-                load4<BYTES>(sm.raw, kS * t - kH, L, R);
+                load4<BYTES>(sm.raw, t, -1, L, R);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     c0.template step<false>(L[q]);
@@ -966,7 +1014,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #pragma unroll 1
             for (int g = 0; g < kS / 4; g++) {
                 int32_t L[4], R[4];
-                load4<BYTES>(sm.raw, kS * t + 4 * g, L, R);
+                load4<BYTES>(sm.raw, t, g, L, R);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     c0.template step<true>(L[q]);
@@ -979,7 +1027,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 // total[k] only counts i >= k (fixed.zig:102-127): take the first terms out again (the history of
                 // thread 0 is the zero pad, so the chain produced exactly these terms); keep the warm-up samples
                 int32_t L[4], R[4];
-                load4<BYTES>(sm.raw, 0, L, R);
+                load4<BYTES>(sm.raw, 0, 0, L, R);
 #define ZF3_FIX(C, SLOT, EXPR)                                                          \
     {                                                                                   \
         int32_t f1p = 0, f2p = 0, f3p = 0, fxp = 0;                                     \
@@ -1017,6 +1065,8 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #undef ZF3_RED
         }
         __syncthreads();
+        // the next frame's ticket: every thread has read the current one by now, and warp 1 only waits for warp 0 here
+        if (t == 32) sm.next_frame = atomicAdd(job.ticket, 1u);
         // ---- decide (one lane per candidate): encoder.zig:482-527, fixed.zig:160-166, rice.zig:97-104 ----
         if (warp == 0) {
             // lane 6 s + k folds value k of candidate s over the warps (k < 5: sum |delta^k x|, k = 5: sample OR); the
@@ -1360,13 +1410,12 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             if (fidx == 0) st_relaxed_gpu(job.desc, kFlagPrefix | (unsigned long long)size);
             else st_relaxed_gpu(job.desc + fidx, kFlagAggregate | (unsigned long long)size);
             if (!fits) atomicOr(job.status, kStatusBitOverflow);
-            // every thread has taken what it needs from the raw PCM (the scan's barrier): fetch the next frame
-            const uint32_t nf = atomicAdd(job.ticket, 1u);
-            sm.next_frame = nf;
+        }
+        {   // every thread has taken what it needs from the raw PCM (the scan's barrier): fetch the next frame
+            const uint32_t nf = __shfl_sync(0xffffffffu, sm.next_frame, 0);
             if (tma && nf < job.n_frames) {
-                fence_proxy_async();
-                mbar_expect_tx(&sm.mbar, frame_bytes);
-                tma_load_1d(sm.raw + kPadWords, job.pcm + (size_t)nf * job.frame_stride, frame_bytes, &sm.mbar);
+                if (t == 0) mbar_expect_tx(&sm.mbar, frame_bytes);
+                fetch_frame<BYTES>(sm, job.pcm + (size_t)nf * job.frame_stride, warp);
             }
         }
         BitW wa, wb;
@@ -1491,7 +1540,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             if (lane == 0) { sm.crc_part[warp] = acc_q; sm.par_part[warp] = par; }
         }
         P.valid = 1; P.fidx = fidx; P.fbytes = fbytes; P.lead = lead; P.fits = fits ? 1u : 0u;
-        f = sm.next_frame;  // written before the last two barriers
+        f = sm.next_frame;  // written behind this frame's first barrier
     }
     if (P.valid) {  // the CTA's last frame
         if (warp == 0) {
