@@ -338,7 +338,7 @@ def main():
     # buffers, upload and download on two streams at once, no kernels (one cudaMemcpyAsync per direction)
     up_s, down_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     d_stage = torch.empty(max(int(got.size), 1), dtype=torch.uint8, device=dev)
-    h_stage = h_out[:max(int(got.size), 1)]
+    h_stage = torch.empty(max(int(got.size), 1), dtype=torch.uint8, pin_memory=True)  # `got` lives in h_out: leave it alone
 
     def bare_copies():
         with torch.cuda.stream(up_s):

@@ -202,6 +202,8 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
 
 void emu_allow_v3(int on) { g_allow_v3 = on; }
 unsigned long long emu_v3_frames(void) { return g_v3_frames; }
+unsigned long long emu_v3_wide_frames(void) { return zf::v3::g_emu_wide_frames; }
+unsigned long long emu_v3_narrow_frames(void) { return zf::v3::g_emu_narrow_frames; }
 
 void emu_best_param_nw(unsigned long long S, unsigned B, unsigned n, unsigned P, unsigned *choice, unsigned long long *cost) {
     uint32_t c, k;

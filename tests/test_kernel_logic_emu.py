@@ -162,3 +162,50 @@ def test_v3_kernel_multi_frame_streams(emu, oracle, bits):
     for name, a, b in signals.stereo_classes(bits, n=2 * 4096):
         _check(emu, oracle, oracle.pcm_bytes_from_int(signals.interleave([a, b]), bits), a.size, bits)
     assert emu.emu_v3_frames() - before >= 15 + 2 * 18  # the streams above really went through the v3 kernel
+
+
+def test_v3_32bit_narrow_and_wide_paths(emu, oracle):
+    """32-bit PCM runs in 32-bit registers while every difference (and the side channel) fits, with exact overflow
+    detection; a frame that overflows is redone by the 64-bit chains.  Both paths, and the boundary between them,
+    against the oracle (fixed.zig:85-167 is i64 throughout; encoder.zig:330-339,398-438 for the 33-bit side)."""
+    emu.emu_v3_wide_frames.restype = C.c_ulonglong
+    emu.emu_v3_narrow_frames.restype = C.c_ulonglong
+    bits, F, n = 32, 1 << 31, 4096
+    rng = np.random.default_rng(32)
+    t = np.arange(n)
+
+    def run(L, R, expect):
+        L = np.clip(np.asarray(L, dtype=np.int64), -F, F - 1)
+        R = np.clip(np.asarray(R, dtype=np.int64), -F, F - 1)
+        w0, n0 = emu.emu_v3_wide_frames(), emu.emu_v3_narrow_frames()
+        _check(emu, oracle, oracle.pcm_bytes_from_int(signals.interleave([L, R]), bits), n, bits, rate=96000)
+        got = "wide" if emu.emu_v3_wide_frames() > w0 else "narrow"
+        assert emu.emu_v3_wide_frames() - w0 + emu.emu_v3_narrow_frames() - n0 == 1
+        assert got == expect, (got, expect)
+
+    loud = (0.98 * F * np.sin(2 * np.pi * 60 * t / 96000)).astype(np.int64)
+    run(loud + rng.integers(-1000, 1000, n), (0.7 * loud).astype(np.int64), "narrow")      # near full scale, smooth
+    run(loud, -loud, "wide")                                                                # |L - R| needs 33 bits
+    run(np.full(n, F - 1), np.full(n, -F), "wide")                                          # constant side of 2^32 - 1
+    run(rng.integers(-F, F, n), rng.integers(-F, F, n), "wide")                             # full-scale noise
+    run(rng.integers(-F // 64, F // 64, n), rng.integers(-F // 64, F // 64, n), "narrow")   # side < 2^26: |delta^4| < 2^30
+    step = np.where(t < 2000, -F + 5, F - 9)                                                # one jump of almost 2^32
+    run(step, step // 3, "wide")
+    jump = np.where(t < 2000, -(F // 2) - 3, F // 2 - 1)                                    # delta^1 = 2^31 - 2 fits, delta^2 does not
+    run(jump, np.zeros(n, np.int64), "wide")
+    small_jump = np.where(t < 2000, -(F // 4), F // 4)                                      # 2^30: only delta^4 = 3 * 2^30 overflows
+    run(small_jump, np.zeros(n, np.int64), "wide")
+    tiny_jump = np.where(t < 2000, -(F // 8), F // 8)                                       # delta^4 = 3 * 2^29 still fits
+    run(tiny_jump, tiny_jump // 2, "narrow")
+    j24 = (rng.integers(-(1 << 23), 1 << 23, n) << 8)                                       # loud 24-bit data in 32 bits
+    run(j24, j24 // 2 // 256 * 256, "wide")
+    q24 = ((0.4 * (1 << 23) * np.sin(t * 0.01)).astype(np.int64) + rng.integers(-50, 50, n)) << 8   # quiet: 8 wasted bits
+    run(q24, q24 // 2 // 256 * 256, "narrow")
+    run(np.full(n, -F), np.full(n, -F), "narrow")                                           # CONSTANT at INT32_MIN, side 0
+    alt = np.where(t % 2 == 0, F // 2 - 1, -(F // 2))                                       # delta^1 = +-(2^31 - 1): fits; delta^2 not
+    run(alt, alt, "wide")
+    # thread 0's first samples: a full-scale first sample is not a difference and must not force the slow path
+    first = np.zeros(n, np.int64)
+    first[0] = F - 1
+    first[1:] = (F - 1) - np.minimum(np.arange(1, n) * 1000, F // 3)
+    run(first, first // 2, "narrow")

@@ -1,13 +1,21 @@
+# The round's standard GPU pass (one gpurun call): smoke, the GPU parity suite, the bench lines of the three single-GPU
+# configs + the reference arm, the ncu launch list of the bench command and one full capture of the dominant kernel per
+# config.  usage: gpurun --timeout 3000 -- 'bash tools/gpu_full_run.sh <tag> [notests]'
 set -x
 cd $GRAFT_REPO_ROOT
 TAG=$1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
+nproc
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; tail -1 gpurun_out/${TAG}_pytest.log
-timeout 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 400 gpurun_out/${TAG}_bench.json
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>&1; tail -c 300 gpurun_out/${TAG}_bench_ref.json
-timeout 300 python bench.py --workload c1_16bit_44k1_60s --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_c1.json 2>&1
-timeout 300 python bench.py --workload c3_32bit_192k_600s --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_c3.json 2>&1
+if [ "$2" != "notests" ]; then
+timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; tail -3 gpurun_out/${TAG}_pytest.log
+fi
+timeout 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 600 gpurun_out/${TAG}_bench.json
+timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${TAG}_bench_ref.json 2>&1; tail -c 300 gpurun_out/${TAG}_bench_ref.json
+timeout 300 python bench.py --workload c1_16bit_44k1_60s --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/${TAG}_bench_c1.json 2>&1; tail -c 300 gpurun_out/${TAG}_bench_c1.json
+timeout 300 python bench.py --workload c3_32bit_192k_600s --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_c3.json 2>&1; tail -c 300 gpurun_out/${TAG}_bench_c3.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 3 --warmup 3 --profile > gpurun_out/${TAG}_ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:v3_kernel -c 1 -o gpurun_out/prof_${TAG}_c2 python bench.py --steps 1 --warmup 3 --profile > gpurun_out/${TAG}_ncu_c2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:v3_kernel -c 1 -o gpurun_out/prof_${TAG}_c3 python bench.py --workload c3_32bit_192k_600s --steps 1 --warmup 3 --profile > gpurun_out/${TAG}_ncu_c3.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:v3_kernel -c 1 -o gpurun_out/prof_${TAG}_c1 python bench.py --workload c1_16bit_44k1_60s --steps 1 --warmup 3 --profile > gpurun_out/${TAG}_ncu_c1.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_c3.log

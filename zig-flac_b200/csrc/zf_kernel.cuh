@@ -1257,13 +1257,12 @@ __global__ void zf_append_tail_kernel(const uint8_t *tail, const uint32_t *tail_
                                       uint32_t fidx, unsigned int *status) {
     const uint32_t size = *tail_size;
     const unsigned long long off = *total;
-    if (off + size > out_cap) {
-        if (threadIdx.x == 0) atomicOr(status, kStatusOutOverflow);
-        return;
-    }
-    for (uint32_t k = threadIdx.x; k < size; k += blockDim.x) out[off + k] = tail[k];
-    __syncthreads();
+    const bool fits = off + size <= out_cap;  // like every frame: one that does not fit is counted, not written
+    if (fits)
+        for (uint32_t k = threadIdx.x; k < size; k += blockDim.x) out[off + k] = tail[k];
+    __syncthreads();  // every thread has read *total
     if (threadIdx.x == 0) {
+        if (!fits) atomicOr(status, kStatusOutOverflow);
         frame_sizes[fidx] = size;
         *total = off + size;
     }

@@ -39,6 +39,10 @@
 namespace zf {
 namespace v3 {
 
+#ifdef ZF_HOST_EMU
+static unsigned long long g_emu_wide_frames = 0, g_emu_narrow_frames = 0;
+#endif
+
 constexpr int kT = 256;          // threads per CTA
 constexpr int kS = 16;           // samples per thread == finest partition (4096 >> 8)
 constexpr int kH = 4;            // history samples in front of a thread's window
@@ -97,7 +101,8 @@ template <int BYTES>
 struct Smem {
     alignas(16) uint32_t raw[Lay<BYTES>::kWords];
     alignas(16) uint32_t bits[BitBufWords<BYTES>::value + 8];
-    alignas(16) uint32_t lvlcost[4][9][16];  // per candidate, per partition order: up to 16 partial cost sums
+    alignas(16) uint32_t lvlcost[4][9][20];  // per candidate, per partition order: up to 16 partial cost sums (rows of
+                                             // 80 bytes: the pick's eight lanes per candidate read them with LDS.128)
     alignas(16) uint8_t lvlfive[4][9][16];   // ... and whether a parameter > 14 occurs (5-bit method, rice.zig:383-387)
     alignas(16) Scratch<BYTES> sc;
     alignas(16) unsigned long long lbwin[128];  // look-back window: descriptors hi-127 .. hi (fetched by cp.async)
@@ -111,6 +116,7 @@ struct Smem {
     uint32_t scan[2][kW];
     uint32_t crc_part[kW], par_part[kW];
     uint32_t next_frame;
+    uint32_t redo;  // 32-bit PCM: the frame overflowed the 32-bit chains, pass 1 is run again in 64 bits
     uint8_t crc8tab[256];
     uint8_t choice[4][512];           // heap node m (1..511) -> Rice parameter, or 0x80 | escape width
 };
@@ -190,8 +196,15 @@ ZF_DEVICE void unpack20(const uint32_t *raw, int t, int32_t (&L)[kXn], int32_t (
     }
 }
 
+// mid = (l + r) >> 1 (encoder.zig:341-349); with 32-bit PCM the sum needs 33 bits, so the floor average is taken without it
+template <int BYTES>
+ZF_DEVICE int32_t mid32(int32_t l, int32_t r) {
+    return BYTES == 4 ? (l & r) + ((l ^ r) >> 1) : (l + r) >> 1;
+}
+
 // candidate channel `slot` (uniform over the block) of a stereo frame: 0 L, 1 R, 2 M = (L + R) >> 1, 3 S = L - R
 // (encoder.zig:330-350).  Every arm produces x directly, so no register copies are needed to merge them.
+// (32-bit PCM comes here only in frames whose side channel and differences fit 32 bits -- see ChainN.)
 template <int BYTES>
 ZF_DEVICE void load_x(const uint32_t *raw, int t, uint32_t slot, int32_t (&x)[kXn]) {
     if (slot == 0) {
@@ -203,7 +216,7 @@ ZF_DEVICE void load_x(const uint32_t *raw, int t, uint32_t slot, int32_t (&x)[kX
         unpack20<BYTES, 0>(raw, t, x, R);
         if (slot == 2) {
 #pragma unroll
-            for (int i = 0; i < kXn; i++) x[i] = (x[i] + R[i]) >> 1;
+            for (int i = 0; i < kXn; i++) x[i] = mid32<BYTES>(x[i], R[i]);
         } else {
 #pragma unroll
             for (int i = 0; i < kXn; i++) x[i] = x[i] - R[i];
@@ -282,6 +295,10 @@ struct Chain {
 
 // the same in 64 bits, with the OR of |delta^k x| that fixed.bestOrder's range check needs (fixed.zig:160-162)
 struct ChainW {
+    typedef long long V;
+    static ZF_DEVICE V mid(int32_t l, int32_t r) { return ((V)l + (V)r) >> 1; }
+    static ZF_DEVICE V side(int32_t l, int32_t r, bool) { return (V)l - (V)r; }
+    ZF_DEVICE uint32_t overflowed() const { return 0; }
     long long xp, e1p, e2p, e3p;
     unsigned long long s0, s1, s2, s3, s4, r0, r1, r2, r3, r4, orv;
 
@@ -314,6 +331,60 @@ struct ChainW {
         if (Q >= 1) { s1 += a1; r1 |= a1; }
         if (Q >= 2) { s2 += a2; r2 |= a2; }
         if (Q >= 3) { s3 += a3; r3 |= a3; }
+    }
+};
+
+// 32-bit PCM in 32-bit registers.  Wrapping 32-bit differences are the true ones as long as every subtraction fits, and
+// whether it does is detected exactly (signed overflow of d = a - b: the sign bit of (a ^ b) & (a ^ d)) provided the
+// operands were true values -- so ONE flag over all orders says "this frame is what the 64-bit chains would have
+// produced"; when it is raised anywhere in the block, pass 1 is redone with ChainW and the frame takes the 64-bit paths.
+// Full-scale square waves, noise and 24-bit material left-justified in 32 bits at high level do that; music does not.
+// Sums of sixteen terms below 2^31 need 64 bits; the range ORs of fixed.zig:160-162 are 32-bit (bit 31 = out of range).
+struct ChainN {
+    typedef int32_t V;
+    static ZF_DEVICE V mid(int32_t l, int32_t r) { return (l & r) + ((l ^ r) >> 1); }
+    // the side channel itself has 33 bits: flag the samples that do not fit (only where they are data: `count`)
+    ZF_DEVICE V side(int32_t l, int32_t r, bool count) {
+        const int32_t d = l - r;
+        if (count) ovf |= (uint32_t)(l ^ r) & (uint32_t)(l ^ d);
+        return d;
+    }
+    ZF_DEVICE uint32_t overflowed() const { return ovf >> 31; }
+    int32_t xp, e1p, e2p, e3p;
+    unsigned long long s0, s1, s2, s3, s4;
+    uint32_t r0, r1, r2, r3, r4, orv, ovf;
+
+    ZF_DEVICE void init() { xp = e1p = e2p = e3p = 0; s0 = s1 = s2 = s3 = s4 = 0; r0 = r1 = r2 = r3 = r4 = orv = ovf = 0; }
+    ZF_DEVICE void diffs(int32_t x, int32_t &e1, int32_t &e2, int32_t &e3, int32_t &e4) {
+        e1 = x - xp; e2 = e1 - e1p; e3 = e2 - e2p; e4 = e3 - e3p;
+    }
+    template <bool ACC>
+    ZF_DEVICE void step(int32_t x) {
+        int32_t e1, e2, e3, e4;
+        diffs(x, e1, e2, e3, e4);
+        if (ACC) {
+            ovf |= ((uint32_t)(x ^ xp) & (uint32_t)(x ^ e1)) | ((uint32_t)(e1 ^ e1p) & (uint32_t)(e1 ^ e2));
+            ovf |= ((uint32_t)(e2 ^ e2p) & (uint32_t)(e2 ^ e3)) | ((uint32_t)(e3 ^ e3p) & (uint32_t)(e3 ^ e4));
+            const uint32_t a0 = uabs(x), a1 = uabs(e1), a2 = uabs(e2), a3 = uabs(e3), a4 = uabs(e4);
+            orv |= (uint32_t)x;
+            s0 += a0; s1 += a1; s2 += a2; s3 += a3; s4 += a4;
+            r0 |= a0; r1 |= a1; r2 |= a2; r3 |= a3; r4 |= a4;
+        }
+        xp = x; e1p = e1; e2p = e2; e3p = e3;
+    }
+    // sample q < 4 of the frame: total[k] and the range OR only count samples i >= k (fixed.zig:102-127); the differences
+    // against the zero pad are not data, so they raise no flag
+    template <int Q>
+    ZF_DEVICE void step_first(int32_t x) {
+        int32_t e1, e2, e3, e4;
+        diffs(x, e1, e2, e3, e4);
+        const uint32_t a0 = uabs(x), a1 = uabs(e1), a2 = uabs(e2), a3 = uabs(e3);
+        orv |= (uint32_t)x;
+        s0 += a0; r0 |= a0;
+        if (Q >= 1) { s1 += a1; r1 |= a1; ovf |= (uint32_t)(x ^ xp) & (uint32_t)(x ^ e1); }
+        if (Q >= 2) { s2 += a2; r2 |= a2; ovf |= (uint32_t)(e1 ^ e1p) & (uint32_t)(e1 ^ e2); }
+        if (Q >= 3) { s3 += a3; r3 |= a3; ovf |= (uint32_t)(e2 ^ e2p) & (uint32_t)(e2 ^ e3); }
+        xp = x; e1p = e1; e2p = e2; e3p = e3;
     }
 };
 
@@ -501,8 +572,9 @@ struct Sub {
 
 // One subframe, counting side.  Fills v[] with what the writing side needs (zigzagged residuals for FIXED, plain residuals
 // where the partition is escaped, shifted samples for VERBATIM) and returns this thread's bit count.  frame_writer.zig:269-372.
-template <int BYTES>
+template <int BYTES, bool W64>
 ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u, uint32_t (&v)[kS]) {
+    typedef typename Arith<W64 ? 4 : 2>::T XT;
     u.choice = 0;
     u.maxq = 0;
     u.vhi = 0;
@@ -510,14 +582,14 @@ ZF_DEVICE uint32_t sub_count(const Smem<BYTES> &sm, int t, uint32_t slot, Sub &u
 #pragma unroll
     for (int j = 0; j < kS; j++) v[j] = 0;
     if (__builtin_expect(u.kind == kConstant, 0)) return t == 0 ? 8u + u.depth_ch : 0u;
-    typename Arith<BYTES>::T x[kXn];
+    XT x[kXn];
     load_x<BYTES>(sm.raw, t, slot, x);
     if (__builtin_expect(u.kind == kVerbatim, 0)) {
 #pragma unroll
         for (int j = 0; j < kS; j++) {
-            const typename Arith<BYTES>::T sv = x[kH + j] >> u.waste;
+            const XT sv = x[kH + j] >> u.waste;
             v[j] = (uint32_t)sv;
-            if (BYTES == 4) u.vhi |= (uint32_t)(((unsigned long long)sv >> 32) & 1ull) << j;
+            if (BYTES == 4) u.vhi |= (sv < 0 ? 1u : 0u) << j;  // bit 32 of a 33-bit field = the sign
         }
         return (uint32_t)kS * u.bps + (t == 0 ? 8u + u.waste : 0u);
     }
@@ -841,6 +913,77 @@ ZF_DEVICE uint32_t header_byte(const uint8_t *crc8tab, int lane, unsigned long l
     return b;
 }
 
+// Pass 1 of 32-bit PCM: fixed.bestOrder's chains (fixed.zig:85-167) two candidates at a time -- trip 0: L, R; trip 1: M, S --
+// with CH = ChainN (32-bit registers, exact overflow flag) or ChainW (64-bit).  Leaves per warp and candidate in sc.red:
+// 5 x 3 sixteen-bit pieces of the sums, 5 x (lo, hi) range ORs, (lo, hi) sample OR, overflow flag.
+template <int BYTES, typename CH>
+ZF_DEVICE void pass1_pairs(Smem<BYTES> &sm, int t, int lane, int warp) {
+    typedef typename CH::V V;
+#pragma unroll 1
+    for (uint32_t trip = 0; trip < 2; trip++) {
+        CH ca, cb;
+        ca.init(); cb.init();
+        {
+            int32_t L[4], R[4];
+            load4<BYTES>(sm.raw, t, -1, L, R);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                ca.template step<false>(trip ? CH::mid(L[q], R[q]) : (V)L[q]);
+                cb.template step<false>(trip ? cb.side(L[q], R[q], false) : (V)R[q]);
+            }
+        }
+        const uint32_t slot_a = trip ? 2u : 0u, slot_b = trip ? 3u : 1u;
+#pragma unroll 1
+        for (int g = 0; g < kS / 4; g++) {
+            int32_t L[4], R[4];
+            load4<BYTES>(sm.raw, t, g, L, R);
+            V xa[4], xb[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                xa[q] = trip ? CH::mid(L[q], R[q]) : (V)L[q];
+                xb[q] = trip ? cb.side(L[q], R[q], true) : (V)R[q];
+            }
+            if (t == 0 && g == 0) {  // the frame's first samples; they are the warm-ups too
+                ca.template step_first<0>(xa[0]); ca.template step_first<1>(xa[1]);
+                ca.template step_first<2>(xa[2]); ca.template step_first<3>(xa[3]);
+                cb.template step_first<0>(xb[0]); cb.template step_first<1>(xb[1]);
+                cb.template step_first<2>(xb[2]); cb.template step_first<3>(xb[3]);
+#pragma unroll
+                for (int q = 0; q < 4; q++) { sm.warm[slot_a][q] = xa[q]; sm.warm[slot_b][q] = xb[q]; }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    ca.template step<true>(xa[q]);
+                    cb.template step<true>(xb[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const CH &C = h ? cb : ca;
+            uint32_t *rp = &sm.sc.red[warp][h ? slot_b : slot_a][0];
+            const unsigned long long sv[5] = {C.s0, C.s1, C.s2, C.s3, C.s4};
+            const unsigned long long rv[5] = {C.r0, C.r1, C.r2, C.r3, C.r4};
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const uint32_t p0 = reduce_add((uint32_t)sv[k] & 0xffffu);
+                const uint32_t p1 = reduce_add((uint32_t)(sv[k] >> 16) & 0xffffu);
+                const uint32_t p2 = reduce_add((uint32_t)(sv[k] >> 32));  // per-thread sums < 2^42
+                const uint32_t o0 = reduce_or((uint32_t)rv[k]), o1 = reduce_or((uint32_t)(rv[k] >> 32));
+                if (lane == 0) {
+                    rp[3 * k] = p0; rp[3 * k + 1] = p1; rp[3 * k + 2] = p2;
+                    rp[15 + 2 * k] = o0; rp[16 + 2 * k] = o1;
+                }
+            }
+            // the sample OR only serves ctz / == 0: a 33-bit side sample has a one among its low 32 bits (|S| < 2^32)
+            const unsigned long long ov = (unsigned long long)(long long)C.orv;
+            const uint32_t w0 = reduce_or((uint32_t)ov), w1 = reduce_or((uint32_t)(ov >> 32));
+            const uint32_t fl = reduce_or(C.overflowed());
+            if (lane == 0) { rp[25] = w0; rp[26] = w1; rp[27] = fl; }
+        }
+    }
+}
+
 // All warps (converged): warp w brings in rows 32 w .. 32 w + 31 of a frame, one bulk copy per group of the padded layout,
 // issued by an elected lane from uniform registers.  Thread 0 arms the barrier with the frame's byte count (a copy that
 // completes first only drives the transaction count negative for a moment; the phase cannot end before that arrival).
@@ -879,10 +1022,8 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         uint4 *bz = reinterpret_cast<uint4 *>(sm.bits);
         const uint4 z = {0, 0, 0, 0};
         for (int k = t; k < (BitBufWords<BYTES>::value + 8) / 4; k += kT) bz[k] = z;
-        for (int k = t; k < 4 * 9 * 16; k += kT) {
-            (&sm.lvlcost[0][0][0])[k] = 0;
-            (&sm.lvlfive[0][0][0])[k] = 0;
-        }
+        for (int k = t; k < 4 * 9 * 20; k += kT) (&sm.lvlcost[0][0][0])[k] = 0;
+        for (int k = t; k < 4 * 9 * 16; k += kT) (&sm.lvlfive[0][0][0])[k] = 0;
         if (t == 0) {
             if (tma) {
                 mbar_init(&sm.mbar, 1);
@@ -931,71 +1072,14 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         // fixed.bestOrder (fixed.zig:85-167) + calcWasteBits' OR (encoder.zig:556-570), streamed: five trips over one
         // piece of code, four inter-channel samples per trip (the first trip runs the chains over the history only),
         // all four candidate channels L, R, M = (L + R) >> 1, S = L - R side by side.
+        bool wide_frame = false;  // 32-bit PCM only: this frame needs the 64-bit paths
+#pragma unroll 1
+        for (;;) {
         if constexpr (WIDE) {
-            // 64-bit chains: two candidates at a time (registers), two trips over the samples
-#pragma unroll 1
-            for (uint32_t trip = 0; trip < 2; trip++) {
-                ChainW ca, cb;  // trip 0: L, R; trip 1: M, S
-                ca.init(); cb.init();
-                {
-                    int32_t L[4], R[4];
-                    load4<BYTES>(sm.raw, t, -1, L, R);
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const long long l = L[q], r = R[q];
-                        ca.template step<false>(trip ? ((l + r) >> 1) : l);
-                        cb.template step<false>(trip ? (l - r) : r);
-                    }
-                }
-                const uint32_t slot_a = trip ? 2u : 0u, slot_b = trip ? 3u : 1u;
-#pragma unroll 1
-                for (int g = 0; g < kS / 4; g++) {
-                    int32_t L[4], R[4];
-                    load4<BYTES>(sm.raw, t, g, L, R);
-                    long long xa[4], xb[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const long long l = L[q], r = R[q];
-                        xa[q] = trip ? ((l + r) >> 1) : l;
-                        xb[q] = trip ? (l - r) : r;
-                    }
-                    if (t == 0 && g == 0) {  // the frame's first samples; they are the warm-ups too
-                        ca.template step_first<0>(xa[0]); ca.template step_first<1>(xa[1]);
-                        ca.template step_first<2>(xa[2]); ca.template step_first<3>(xa[3]);
-                        cb.template step_first<0>(xb[0]); cb.template step_first<1>(xb[1]);
-                        cb.template step_first<2>(xb[2]); cb.template step_first<3>(xb[3]);
-#pragma unroll
-                        for (int q = 0; q < 4; q++) { sm.warm[slot_a][q] = xa[q]; sm.warm[slot_b][q] = xb[q]; }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            ca.template step<true>(xa[q]);
-                            cb.template step<true>(xb[q]);
-                        }
-                    }
-                }
-#define ZF3_REDW(C, SLOT)                                                                        \
-    {                                                                                            \
-        uint32_t *rp = &sc.red[warp][SLOT][0];                                                   \
-        const unsigned long long sv[5] = {C.s0, C.s1, C.s2, C.s3, C.s4};                         \
-        const unsigned long long rv[5] = {C.r0, C.r1, C.r2, C.r3, C.r4};                         \
-        _Pragma("unroll") for (int k = 0; k < 5; k++) {                                          \
-            const uint32_t p0 = reduce_add((uint32_t)sv[k] & 0xffffu);                           \
-            const uint32_t p1 = reduce_add((uint32_t)(sv[k] >> 16) & 0xffffu);                   \
-            const uint32_t p2 = reduce_add((uint32_t)(sv[k] >> 32));  /* per-thread sums < 2^42 */ \
-            const uint32_t o0 = reduce_or((uint32_t)rv[k]), o1 = reduce_or((uint32_t)(rv[k] >> 32)); \
-            if (lane == 0) {                                                                     \
-                rp[3 * k] = p0; rp[3 * k + 1] = p1; rp[3 * k + 2] = p2;                          \
-                rp[15 + 2 * k] = o0; rp[16 + 2 * k] = o1;                                        \
-            }                                                                                    \
-        }                                                                                        \
-        const uint32_t w0 = reduce_or((uint32_t)C.orv), w1 = reduce_or((uint32_t)(C.orv >> 32)); \
-        if (lane == 0) { rp[25] = w0; rp[26] = w1; }                                             \
-    }
-                ZF3_REDW(ca, slot_a)
-                ZF3_REDW(cb, slot_b)
-#undef ZF3_REDW
-            }
+            // 32-bit PCM: two candidates at a time (registers), two trips over the samples -- in 32-bit registers with
+            // exact overflow detection (ChainN) first; a frame that raises the flag comes back here for the 64-bit chains
+            if (wide_frame) pass1_pairs<BYTES, ChainW>(sm, t, lane, warp);
+            else pass1_pairs<BYTES, ChainN>(sm, t, lane, warp);
         } else
         {
             Chain c0, c1, c2, c3;
@@ -1065,14 +1149,22 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #undef ZF3_RED
         }
         __syncthreads();
-        // the next frame's ticket: every thread has read the current one by now, and warp 1 only waits for warp 0 here
-        if (t == 32) sm.next_frame = atomicAdd(job.ticket, 1u);
+        if (!wide_frame) {
+            // the next frame's ticket: every thread has read the current one by now, and warp 1 only waits for warp 0 here
+            if (t == 32) sm.next_frame = atomicAdd(job.ticket, 1u);
+            // ... and so does the last warp: it fetches the look-back window of the previous frame and examines it (round 1)
+            if (P.valid && warp == kW - 1) {
+                lb_start(sm, lba, lane, P);
+                if (!sm.lb_done) lb_step(sm, lba, lane, P);
+            }
+        }
         // ---- decide (one lane per candidate): encoder.zig:482-527, fixed.zig:160-166, rice.zig:97-104 ----
         if (warp == 0) {
             // lane 6 s + k folds value k of candidate s over the warps (k < 5: sum |delta^k x|, k = 5: sample OR); the
             // six values of a candidate are then exchanged inside its lane group
             const uint32_t s = (uint32_t)lane / 6u, kk = (uint32_t)lane % 6u;
             unsigned long long mine = 0, mine_rng = 0;
+            uint32_t ovf_any = 0;
             if (lane < 24) {
                 if constexpr (WIDE) {
                     if (kk < 5) {
@@ -1088,7 +1180,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                     } else {
                         uint32_t o0 = 0, o1 = 0;
 #pragma unroll
-                        for (int w = 0; w < kW; w++) { o0 |= sc.red[w][s][25]; o1 |= sc.red[w][s][26]; }
+                        for (int w = 0; w < kW; w++) { o0 |= sc.red[w][s][25]; o1 |= sc.red[w][s][26]; ovf_any |= sc.red[w][s][27]; }
                         mine = (unsigned long long)o0 | ((unsigned long long)o1 << 32);
                     }
                 } else {
@@ -1148,8 +1240,25 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             }
             sm.dec[s] = d;
             }
+            if constexpr (WIDE) {
+                const uint32_t any = __ballot_sync(0xffffffffu, ovf_any != 0);
+                if (lane == 0) sm.redo = (!wide_frame && any) ? 1u : 0u;
+            }
         }
         __syncthreads();
+        if constexpr (WIDE) {
+            if (!wide_frame && sm.redo) {  // block-uniform
+                wide_frame = true;
+                continue;
+            }
+        }
+        break;
+        }  // pass 1 + decide
+        bool use_wide = false;
+        if constexpr (WIDE) use_wide = wide_frame;
+#ifdef ZF_HOST_EMU
+        if (t == 0) (use_wide ? g_emu_wide_frames : g_emu_narrow_frames)++;  // test harness: which path a frame took
+#endif
 
         // ================= pass 2: leaf statistics of the chosen order, level-8 search, tree levels 7..3 ==========
         {
@@ -1168,7 +1277,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             MX = r > MX ? r : MX;                                                                   \
         }                                                                                           \
     }
-            if constexpr (WIDE) {
+            if (use_wide) {
                 // 64-bit residual chains, one candidate per trip; the residual itself is the low 32 bits (fixed.zig:70-73)
 #pragma unroll 1
                 for (uint32_t s = 0; s < 4; s++) {
@@ -1215,13 +1324,13 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #pragma unroll
                     for (int i = 0; i < kXn; i++) {
                         const int32_t sd = A[i] - B[i];
-                        B[i] = (A[i] + B[i]) >> 1;
+                        B[i] = mid32<BYTES>(A[i], B[i]);
                         A[i] = sd;
                     }
                 }
                 const uint32_t slot_a = it ? 0u : 3u, slot_b = it ? 1u : 2u;
                 const bool fix_a = sm.dec[slot_a].kind == kFixed, fix_b = sm.dec[slot_b].kind == kFixed;
-                uint32_t sum_a = 0, sum_b = 0;
+                typename Arith<BYTES>::U sum_a = 0, sum_b = 0;  // sixteen residuals below 2^31 each with 32-bit PCM
                 int32_t mn_a = 0, mx_a = 0, mn_b = 0, mx_b = 0;
                 if (fix_a) ZF3_LEAF(slot_a, A, sum_a, mn_a, mx_a)
                 if (fix_b) ZF3_LEAF(slot_b, B, sum_b, mn_b, mx_b)
@@ -1235,9 +1344,10 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                     const int32_t mn = (h ? mn_b : mn_a) >> waste, mx = (h ? mx_b : mx_a) >> waste;
                     const uint32_t zm = zigzag(mn), zx = zigzag(mx);
                     uint32_t B = bitlen32(zm > zx ? zm : zx);        // bit length of the OR of the zigzags
-                    const uint32_t S32 = (h ? sum_b : sum_a) >> waste;  // rice.calcSums, rice.zig:288-340
+                    const typename Arith<BYTES>::U S32 = (h ? sum_b : sum_a) >> waste;  // rice.calcSums, rice.zig:288-340
                     uint32_t choice, cost;
-                    best_param_32(S32, B, (uint32_t)kS - jstart, P, choice, cost);
+                    if constexpr (WIDE) best_param_w(S32, B, (uint32_t)kS - jstart, P, choice, cost);
+                    else best_param_32(S32, B, (uint32_t)kS - jstart, P, choice, cost);
                     sm.choice[slot][256 + t] = (uint8_t)choice;
                     const uint32_t wc = reduce_add(cost);
                     const uint32_t wf = __ballot_sync(0xffffffffu, choice < 0x80u && choice > 14u);
@@ -1256,7 +1366,8 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             }
 #undef ZF3_LEAF
         }
-        if (P.valid && warp == kW - 1) lb_start(sm, lba, lane, P);  // fetch the previous frame's look-back window meanwhile
+        // round 2 of the look-back, if round 1 did not reach a prefix: its window has arrived during pass 2
+        if (P.valid && warp == kW - 1 && !sm.lb_done) lb_step(sm, lba, lane, P);
         __syncthreads();
         // ================= round B: heap nodes 1..255 (levels 0..7), one per thread =================
         {
@@ -1392,8 +1503,14 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 
         // ================= pack: count, scan, publish, write =================
         uint32_t va[kS], vb[kS];
-        const uint32_t len_a = sub_count<BYTES>(sm, t, sa, ua, va);
-        const uint32_t len_b = sub_count<BYTES>(sm, t, sb, ub, vb);
+        uint32_t len_a, len_b;
+        if (use_wide) {
+            len_a = sub_count<BYTES, true>(sm, t, sa, ua, va);
+            len_b = sub_count<BYTES, true>(sm, t, sb, ub, vb);
+        } else {
+            len_a = sub_count<BYTES, false>(sm, t, sa, ua, va);
+            len_b = sub_count<BYTES, false>(sm, t, sb, ub, vb);
+        }
         uint32_t ex_a, ex_b, tot_a, tot_b;
         block_scan2(sm.scan, t, len_a, len_b, ex_a, ex_b, tot_a, tot_b);
         // 4 fixed bytes + the UTF-8-like frame number + CRC-8 (block size 4096 and table sample rates have no trailer)
