@@ -30,7 +30,7 @@ enum {
     ZF_OK = 0,
     ZF_ERR_INVALID_ARG = -1,   /* NULL pointer, zero block size, > 8 channels, ... (asserts encoder.zig:49-51) */
     ZF_ERR_UNSUPPORTED = -2,   /* configuration the reference cannot encode either, or outside this build
-                                  (bit depth not 16/24/32, block_size > 4096, frame number >= 2^31) */
+                                  (bit depth not 8/16/24/32, block_size > 4096, frame number >= 2^31) */
     ZF_ERR_NO_DEVICE = -3,     /* no CUDA device / not sm_100 -- there is no CPU fallback */
     ZF_ERR_CUDA = -4,          /* CUDA runtime error; zf_last_cuda_error() has the text */
     ZF_ERR_NOMEM = -5,         /* Allocator.Error (encoder.zig:48) */
@@ -53,7 +53,8 @@ enum {
 typedef struct zf_config {
     uint32_t struct_size;          /* sizeof(zf_config), for ABI evolution */
     uint16_t block_size;           /* Config.block_size; reference default 4096 (encoder.zig:644) */
-    uint8_t bit_depth;             /* 16, 24 or 32 */
+    uint8_t bit_depth;             /* 8, 16, 24 or 32; PCM is bit_depth/8 bytes per sample, little-endian, signed (8-bit
+                                      too: see zf_wav8_to_samples) */
     uint8_t channels;              /* 1..8; 2 + stereo_decorrelation selects L/R, L/S, S/R, M/S per frame */
     uint32_t sample_rate;          /* FrameInfo.sample_rate */
     uint8_t stereo_decorrelation;  /* Feature.stereo_decorrelation */
@@ -172,6 +173,21 @@ typedef struct zf_md5 {
 void zf_md5_init(zf_md5 *m);
 void zf_md5_update(zf_md5 *m, const uint8_t *data, size_t len);
 void zf_md5_final(zf_md5 *m, uint8_t digest[16]);
+
+/* Optional libcrypto MD5, the counterpart of the reference's `-Dlink_ossl` build option (md5.zig:3-35, build.zig:10-18):
+ * the library dlopen()s libcrypto on demand; the whole-file driver uses it when ZF_MD5=openssl is set in the environment.
+ * Returns 1 when MD5_Init/Update/Final were found. */
+int zf_md5_openssl_available(void);
+
+/* WavReader.fillSamples for one-byte containers (wav_reader.zig:56-90): raw WAV bytes -> the signed samples the reference's
+ * reader leaves in Encoder.samples, interleaved, one byte each -- the input of zf_encode_pcm at bit_depth 8.  The
+ * reference subtracts 128 from the unshifted plane word (:71-78), so a sample is (int8)(byte - borrow) with borrow = 1
+ * iff the plane's previous content at that (channel, index in block) was non-negative (1 in a fresh plane): `state`
+ * (block_size * channels bytes, zf_wav8_state_init) carries that from call to call; first_sample is the stream position
+ * of raw[0].  Serial by nature, host only. */
+void zf_wav8_state_init(uint8_t *state, size_t n);
+void zf_wav8_to_samples(const uint8_t *raw, uint64_t samples_per_channel, uint32_t channels, uint32_t block_size,
+                        uint64_t first_sample, uint8_t *state, int8_t *out);
 
 /* WavReader.getFmt -- wav_reader.zig:116-170 */
 typedef struct zf_wav_format {

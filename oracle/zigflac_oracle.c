@@ -923,9 +923,18 @@ void zo_bytes_to_planes(zo_encoder *e, const uint8_t *bytes, size_t n_samples, u
             e->samples[ch][i] = (int32_t)v;
         }
     }
-    /* the 8-bit "unsigned to signed" step (:71-78) subtracts from the unshifted word and depends on
-     * stale plane contents; 8-bit input is outside every supported configuration and is rejected
-     * by the callers of this function. */
+    /* "Unsigned to signed", :71-78: 128 >> (8 - bit_depth) is subtracted from the UNSHIFTED word, whose low 24 bits
+     * are whatever the plane held before (the previous frame's sample at this index, shifted by that frame's wasted
+     * bits; zero in a fresh allocation -- this restatement callocs the planes, as fresh pages from the OS are).
+     * The subtraction therefore only ever borrows one from the byte: the sample becomes (int8)(byte - borrow),
+     * borrow = 1 iff the stale word was non-negative.  A latent bug of the reference (the byte is read as two's
+     * complement, not as offset binary), reproduced as it is: the frames decode to exactly these samples. */
+    if (bytes_per_sample == 1) {
+        const int32_t sub_amt = (int32_t)128 >> (8u - bit_depth);
+        for (unsigned ch = 0; ch < channels; ch++)
+            for (size_t i = 0; i < n_samples; i++)
+                e->samples[ch][i] = (int32_t)((uint32_t)e->samples[ch][i] - (uint32_t)sub_amt);
+    }
     if (bit_depth != 32) { /* :81-88 */
         const unsigned shift_amt = 32u - bit_depth;
         for (unsigned ch = 0; ch < channels; ch++)
@@ -1055,7 +1064,8 @@ size_t zo_write_vorbis_comment(int last_metadata, uint8_t out[31]) { /* encoder.
 /* wav2flac.zig: the frame loop and the whole-file driver                                       */
 /* ------------------------------------------------------------------------------------------ */
 
-static int frame_bit_depth_supported(unsigned d) { return d == 16 || d == 24 || d == 32; }
+/* 8, 16, 24, 32: the depths frame_writer.zig:221-233 has a header code for (4/12/20 hit `unreachable` there) */
+static int frame_bit_depth_supported(unsigned d) { return d == 8 || d == 16 || d == 24 || d == 32; }
 
 /* host-thread sharding of the frame loop (frames are independent; the reference itself is single-threaded) */
 typedef struct {
@@ -1107,6 +1117,7 @@ size_t zo_encode_pcm(const zo_config *cfg, uint32_t sample_rate, const uint8_t *
     if (n_frames) *n_frames = (uint32_t)frames;
     if (frames == 0) return 0;
     if (n_threads < 1) n_threads = 1;
+    if (cfg->bit_depth == 8) n_threads = 1; /* 8-bit samples depend on the previous frame's plane (zo_bytes_to_planes) */
     int failed = 0;
 
     if (n_threads == 1) { /* the reference's own shape: one encoder, frames strictly in order */
@@ -1159,7 +1170,7 @@ int zo_wav_to_flac(const uint8_t *wav, size_t wav_len, uint8_t **flac, size_t *f
     if (fmt.bit_depth < 4 || fmt.bit_depth > 32 || fmt.channels == 0 || fmt.channels > 8 ||
         fmt.sample_rate >= (1u << 20))
         return 2;
-    if (!frame_bit_depth_supported(fmt.bit_depth)) return 2; /* 4/8/12/20-bit: unreachable/UB upstream */
+    if (!frame_bit_depth_supported(fmt.bit_depth)) return 2; /* 4/12/20-bit: `unreachable` upstream */
     zo_streaminfo si;
     zo_streaminfo_init(&si);
     si.sample_rate = fmt.sample_rate;

@@ -111,6 +111,7 @@ void run_block(void (*fn)(void *), void *arg, int nthreads) {
 static zf::FrameJob g_job;
 static int g_bytes, g_full, g_indep, g_v3;
 static int g_allow_v3 = 1;
+static unsigned g_bit_depth = 0;  // 0 = 8 x container bytes
 static unsigned long long g_v3_frames = 0;
 
 static void kernel_entry(void *) {
@@ -173,13 +174,14 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     j.batch_frames = (uint32_t)frames; j.first_frame_number = first_frame_number;
     j.frame_stride = block_size * channels * bytes_per_sample; j.sample_rate = sample_rate; j.channels = channels;
     j.max_rice_order = max_rice_order; j.max_rice_param = max_rice_param; j.use_tma = 1;
+    j.bit_depth = g_bit_depth;
     g_bytes = bytes_per_sample;
     if (full) {
         j.pcm = pcm; j.n_frames = (uint32_t)full; j.frame_base = 0; j.block_size = block_size;
-        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8;
+        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8 && g_bit_depth == 0;
         bool table = false;
         for (unsigned r : {88200u, 176400u, 192000u, 8000u, 16000u, 22050u, 24000u, 32000u, 44100u, 48000u, 96000u}) table |= r == sample_rate;
-        g_v3 = g_full && g_allow_v3 && max_rice_param == 30 && table;
+        g_v3 = g_full && g_allow_v3 && max_rice_param == 30 && table && g_bit_depth == 0;
         g_job = j;
         ticket = 0;
         if (g_v3) g_v3_frames += full;
@@ -201,6 +203,7 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
 }
 
 void emu_allow_v3(int on) { g_allow_v3 = on; }
+void emu_set_bit_depth(unsigned d) { g_bit_depth = d; }
 unsigned long long emu_v3_frames(void) { return g_v3_frames; }
 unsigned long long emu_v3_wide_frames(void) { return zf::v3::g_emu_wide_frames; }
 unsigned long long emu_v3_narrow_frames(void) { return zf::v3::g_emu_narrow_frames; }

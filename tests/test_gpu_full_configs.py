@@ -199,3 +199,35 @@ def test_cli_binary_exit_codes(zf, oracle, tmp_path):
     assert b"flac does not support this wav format" in r.stderr
     rc_o, _ = oracle.wav_to_flac(bad.read_bytes())
     assert rc_o == 2
+
+
+@pytest.mark.parametrize("channels", [1, 2, 5])
+def test_8bit_wav(zf, oracle, channels):
+    """8-bit WAV (wav_reader.zig:71-88 with the subtract-from-the-unshifted-word quirk, frame header depth code 2):
+    whole file == the oracle's file; the batched entry on the reader's signed samples == the oracle's frames."""
+    rng = np.random.default_rng(80 + channels)
+    n = 22050 * 3 + 321
+    t = np.arange(n)
+    cols = []
+    for c in range(channels):
+        k = c % 3
+        if k == 0:
+            v = np.clip(128 + 100 * np.sin(t * 0.01 * (c + 1)) + rng.integers(-2, 3, n), 0, 255)
+        elif k == 1:
+            v = rng.integers(0, 256, n)
+        else:
+            v = np.where((t // 900) % 3 == 0, 0, np.where((t // 900) % 3 == 1, 128, 64 + (t % 7)))
+        cols.append(v.astype(np.uint8))
+    raw = np.stack(cols, axis=1).reshape(-1).copy()
+    wav = oracle.make_wav(raw.tobytes(), channels, 8, 22050)
+    rc_ref, ref = oracle.wav_to_flac(wav)
+    rc, got = zf.wav_to_flac(wav)
+    assert rc == 0 and rc_ref == 0
+    assert got == ref
+    signed = zf.Wav8Reader(channels).convert(raw)
+    d = oracle.decode(got)
+    assert d["rc"] == 0 and np.array_equal(d["pcm"], signed.astype(np.int32))
+    fr, fs = oracle.encode_pcm(raw, n, oracle.config(channels, 8), 22050, 0)
+    with zf.Encoder(zf.Config.default(channels, 8), 22050, max_frames_per_batch=7) as enc:
+        g, gs = enc.encode_pcm(signed, n, 0)
+    assert np.array_equal(gs, fs) and g.tobytes() == fr.tobytes()

@@ -163,3 +163,32 @@ def test_reference_arm_maps_no_product_library():
     import bench
     assert line["config"] == bench.make_config("c1_16bit_44k1_60s", 1)
     assert line["config"]["l2_resident"] is True
+
+
+def test_wav8_reader_matches_the_oracle_restatement(zf, oracle):
+    """One-byte WAV samples (wav_reader.zig:56-90): the reference subtracts 128 from the unshifted plane word, so every
+    sample depends on what the plane held one frame earlier.  The product's closed form (zf_wav8_to_samples) against
+    the oracle, which restates the reference's word arithmetic on planes it keeps from frame to frame: the oracle's
+    stream must decode (independent decoder) to exactly the product reader's samples."""
+    rng = np.random.default_rng(8)
+    for channels in (1, 2, 3):
+        n = 3 * 4096 + 1234
+        t = np.arange(n)
+        planes = []
+        for c in range(channels):
+            if c == 0:
+                v = np.clip(128 + 90 * np.sin(t * 0.013) + rng.integers(-4, 5, n), 0, 255)
+            elif c == 1:
+                v = rng.integers(0, 256, n)                       # every byte value, the -128 / borrow wrap included
+            else:
+                v = np.where((t // 700) % 2 == 0, 0, 128)        # runs of 0x00 (borrow chains) and of 0x80
+            planes.append(v.astype(np.uint8))
+        raw = np.stack(planes, axis=1).reshape(-1).copy()
+        wav = oracle.make_wav(raw.tobytes(), channels, 8, 22050)
+        rc, flac = oracle.wav_to_flac(wav)
+        assert rc == 0
+        d = oracle.decode(flac)
+        assert d["rc"] == 0 and d["streaminfo"].bits == 8
+        rd = zf.Wav8Reader(channels)
+        got = np.concatenate([rd.convert(raw[:5000 * channels]), rd.convert(raw[5000 * channels:])])  # state carries over
+        assert np.array_equal(got.astype(np.int32), d["pcm"])

@@ -209,3 +209,28 @@ def test_v3_32bit_narrow_and_wide_paths(emu, oracle):
     first[0] = F - 1
     first[1:] = (F - 1) - np.minimum(np.arange(1, n) * 1000, F // 3)
     run(first, first // 2, "narrow")
+
+
+def test_8bit_samples_through_the_16bit_kernels(emu, oracle):
+    """bit_depth 8: signed one-byte samples travel in 16-bit containers through the general kernels with depth 8
+    (frame header code 2, frame_writer.zig:221-233; Rice limits from bps <= 9).  Stereo and mono against the oracle,
+    which reads the raw unsigned bytes the way the reference's reader does."""
+    import zigflac_b200 as zf
+    rng = np.random.default_rng(88)
+    emu.emu_set_bit_depth.argtypes = [C.c_uint]
+    try:
+        for channels in (2, 1):
+            n = 2 * 4096 + 777
+            t = np.arange(n)
+            cols = [np.clip(128 + 100 * np.sin(t * 0.01 * (c + 1)) + rng.integers(-2, 3, n), 0, 255).astype(np.uint8)
+                    for c in range(channels)]
+            raw = np.stack(cols, axis=1).reshape(-1).copy()
+            ref, rs = oracle.encode_pcm(raw, n, oracle.config(channels, 8), 22050, 0)
+            signed = zf.Wav8Reader(channels).convert(raw)
+            wide = signed.astype("<i2").view(np.uint8)
+            emu.emu_set_bit_depth(8)
+            got, gs = _emu_encode(emu, wide, n, 16, channels=channels, rate=22050)
+            assert np.array_equal(rs, gs)
+            assert ref.tobytes() == got.tobytes()
+    finally:
+        emu.emu_set_bit_depth(0)

@@ -119,6 +119,11 @@ def _lib():
     L.zf_md5_update.restype = None
     L.zf_md5_final.argtypes = [C.POINTER(ZfMd5), u8p]
     L.zf_md5_final.restype = None
+    L.zf_md5_openssl_available.restype = C.c_int
+    L.zf_wav8_state_init.argtypes = [vp, C.c_size_t]
+    L.zf_wav8_state_init.restype = None
+    L.zf_wav8_to_samples.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, vp, vp]
+    L.zf_wav8_to_samples.restype = None
     L.zf_wav_parse.argtypes = [vp, C.c_size_t, C.POINTER(ZfWavFormat)]
     L.zf_encode_wav_file.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_int]
     L.zf_encode_wav_memory.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.c_int]
@@ -438,6 +443,25 @@ def synth_pcm(samples, sample_rate, bit_depth, first_sample=0, seed=0x5EED, thre
     if rc != 0:
         raise ValueError("synth_pcm: unsupported format")
     return out
+
+
+class Wav8Reader:
+    """WavReader.fillSamples for one-byte containers (wav_reader.zig:56-90): raw WAV bytes -> the signed samples the
+    reference's reader produces (zf_wav8_to_samples), with the state it carries from frame to frame."""
+
+    def __init__(self, channels, block_size=4096):
+        self.channels, self.block_size, self.pos = channels, block_size, 0
+        self.state = np.empty(block_size * channels, dtype=np.uint8)
+        _lib().zf_wav8_state_init(self.state.ctypes.data, self.state.size)
+
+    def convert(self, raw):
+        raw = _u8(raw)
+        n = raw.size // self.channels
+        out = np.empty(n * self.channels, dtype=np.int8)
+        _lib().zf_wav8_to_samples(raw.ctypes.data, n, self.channels, self.block_size, self.pos, self.state.ctypes.data,
+                                  out.ctypes.data)
+        self.pos += n
+        return out
 
 
 def device_available(device_id=0):

@@ -42,6 +42,7 @@ constexpr int kRing = 256;  // covers the largest frame of the multi-channel pat
 
 struct Slot {  // one in-flight batch: device buffers + pinned staging
     uint8_t *d_pcm = nullptr;
+    uint8_t *d_wide = nullptr;  // 8-bit input widened to 16-bit containers
     uint8_t *d_out = nullptr;
     uint8_t *h_pcm = nullptr;   // pinned
     uint8_t *h_out = nullptr;   // pinned
@@ -81,7 +82,8 @@ struct zf_encoder {
     cudaStream_t s_up = nullptr, s_down = nullptr;  // all uploads / all downloads, each in batch order on its own stream
     cudaEvent_t ev_dev = nullptr;  // end of the last zf_encode_device batch: it shares slot 0's control block and descriptors
     bool dev_pending = false;
-    size_t frame_pcm_bytes = 0;
+    size_t frame_pcm_bytes = 0;   // one frame of the caller's PCM
+    size_t frame_dev_bytes = 0;   // ... and as the kernels read it (differs for 8-bit samples)
     size_t max_frame_bytes = 0;
     bool stereo = false;
     bool force_legacy = false;  // ZF_LEGACY_KERNEL=1: A/B against the 512-thread kernel (development aid)
@@ -112,7 +114,9 @@ void tr_host(zf_encoder *e, uint64_t batch, int point) {
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - e->tr_h0).count();
 }
 
-bool depth_ok(unsigned d) { return d == 16 || d == 24 || d == 32; }
+bool depth_ok(unsigned d) { return d == 8 || d == 16 || d == 24 || d == 32; }
+// bytes per sample inside the kernels: 8-bit samples are widened to 16-bit containers on the device first
+int container_bytes(const zf_config &cfg) { return cfg.bit_depth == 8 ? 2 : cfg.bit_depth / 8; }
 
 // sample rates with a frame-header code of their own (frame_writer.zig:187-217); others take the general kernels
 bool table_rate(uint32_t r) {
@@ -164,7 +168,7 @@ int setup_indep_kernel(zf_encoder *e, int *occ) {
 }
 
 int setup_kernels(zf_encoder *e) {
-    const int bytes = e->cfg.bit_depth / 8;
+    const int bytes = container_bytes(e->cfg);
     int rc = ZF_OK;
     if (e->stereo) {
         if (bytes == 2) { rc = setup_stereo_kernel<2, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<2, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<2>(e, &e->occ_v3); }
@@ -208,7 +212,7 @@ void launch_stereo(bool full, int grid, size_t smem, cudaStream_t s, bool overla
 }
 
 void launch_one(zf_encoder *e, bool full, int grid, cudaStream_t s, const zf::FrameJob &job, bool overlap = false) {
-    const int bytes = e->cfg.bit_depth / 8;
+    const int bytes = container_bytes(e->cfg);
     if (e->stereo) {
         if (bytes == 2) launch_stereo<2>(full, grid, e->smem_stereo, s, overlap, job);
         else if (bytes == 3) launch_stereo<3>(full, grid, e->smem_stereo, s, overlap, job);
@@ -247,13 +251,22 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     job.pow8 = e->d_pow8;
     job.batch_frames = (uint32_t)frames;
     job.first_frame_number = first_frame_number;
-    job.frame_stride = (uint32_t)e->frame_pcm_bytes;
+    job.frame_stride = (uint32_t)e->frame_dev_bytes;
+    job.bit_depth = e->cfg.bit_depth;
     job.sample_rate = e->cfg.sample_rate;
     job.channels = e->cfg.channels;
     job.max_rice_order = e->cfg.max_rice_order;
     job.max_rice_param = e->cfg.max_rice_param;
-    // the fast kernel covers the reference's default shape: 4096-sample frames, max_rice_order 8
-    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.max_rice_order == 8;
+    if (e->cfg.bit_depth == 8) {  // one signed byte per sample in, 16-bit containers for the kernels
+        if (!sl.d_wide) ZF_CUDA(cudaMalloc(&sl.d_wide, (size_t)e->cfg.max_frames_per_batch * e->frame_dev_bytes));
+        const unsigned long long count = samples * e->cfg.channels;
+        const int blocks = (int)std::min<unsigned long long>((count + 255) / 256, 4096);
+        zf::zf_widen8_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const int8_t *>(d_pcm), reinterpret_cast<int16_t *>(sl.d_wide), count);
+        d_pcm = sl.d_wide;
+        (*launches)++;
+    }
+    // the fast kernel covers the reference's default shape: 4096-sample frames, max_rice_order 8, 16/24/32-bit samples
+    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.max_rice_order == 8 && e->cfg.bit_depth != 8;
     // the 1-D TMA bulk copy needs 16-byte aligned sources; frame strides are multiples of 16 already
     job.use_tma = ((uintptr_t)d_pcm & 15u) == 0 ? 1u : 0u;
     // The short last frame is a one-CTA launch of the general kernel IN FRONT of the persistent full-frame kernel, which is
@@ -264,7 +277,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     if (full) ZF_CUDA(cudaEventRecord(sl.kev[2 * ring], s));
     if (split_tail) {
         zf::FrameJob tj = job;
-        tj.pcm = d_pcm + full * e->frame_pcm_bytes;
+        tj.pcm = d_pcm + full * e->frame_dev_bytes;
         tj.out = sl.d_tail;
         tj.out_cap = e->max_frame_bytes + 64;
         tj.frame_sizes = reinterpret_cast<uint32_t *>(sl.d_tail_meta + 2);
@@ -357,6 +370,7 @@ int slot_init(zf_encoder *e, Slot &sl) {
 void slot_free(Slot &sl) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     cudaFree(sl.d_tail);
+    cudaFree(sl.d_wide);
     cudaFree(sl.d_pcm); cudaFree(sl.d_out); cudaFree(sl.d_sizes); cudaFree(sl.d_ctl_block); cudaFree(sl.d_total);
     cudaFreeHost(sl.h_pcm); cudaFreeHost(sl.h_out); cudaFreeHost(sl.h_sizes); cudaFreeHost(sl.h_total);
     if (sl.ev_start) cudaEventDestroy(sl.ev_start);
@@ -538,7 +552,7 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     // asserts of Encoder.init, encoder.zig:49-51
     if (cfg->block_size == 0 || cfg->channels == 0 || cfg->channels > 8 || cfg->bit_depth == 0 || cfg->bit_depth % 4 != 0)
         return ZF_ERR_INVALID_ARG;
-    if (!depth_ok(cfg->bit_depth)) return ZF_ERR_UNSUPPORTED;          // 4/8/12/20-bit: unreachable upstream
+    if (!depth_ok(cfg->bit_depth)) return ZF_ERR_UNSUPPORTED;          // 4/12/20-bit: `unreachable` upstream (frame_writer.zig:221-233)
     if (cfg->block_size > zf::kMaxBlock) return ZF_ERR_UNSUPPORTED;    // one CTA holds at most 4096 samples/channel
     if (cfg->max_rice_order > 8) return ZF_ERR_UNSUPPORTED;            // rice.MAX_ORDER = 8 (rice.zig:12)
     if (cfg->max_rice_param == 0 || cfg->max_rice_param > 30) return ZF_ERR_UNSUPPORTED;  // 0: overflow upstream
@@ -554,6 +568,7 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     { const char *tr = getenv("ZF_TRACE"); e->trace = tr && tr[0] == '1'; }
     { const char *nt = getenv("ZF_NO_TAPER"); e->no_taper = nt && nt[0] == '1'; }  // A/B of the batch plan (development aid)
     e->frame_pcm_bytes = (size_t)cfg->block_size * cfg->channels * (cfg->bit_depth / 8);
+    e->frame_dev_bytes = (size_t)cfg->block_size * cfg->channels * container_bytes(*cfg);
     e->max_frame_bytes = max_frame_bytes_of(cfg);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device_id) != cudaSuccess) { delete e; return ZF_ERR_CUDA; }

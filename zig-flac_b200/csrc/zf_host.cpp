@@ -164,6 +164,79 @@ size_t zf_write_vorbis_comment(int last_metadata, uint8_t out[31]) {
     return 8 + vlen + 4;
 }
 
+// ---- WavReader.fillSamples for one-byte containers, wav_reader.zig:56-90 -----------------------------------------
+// The reference writes the byte into the top of the plane word, subtracts 128 from the UNSHIFTED word (:71-78) and
+// shifts down (:81-88).  The low 24 bits of that word are what the plane held before -- the previous frame's sample
+// at this index (possibly shifted by that frame's wasted bits, which keeps its sign) or zero in the fresh allocation --
+// so the subtraction borrows one from the byte exactly when that stale value was non-negative:
+//     sample = (int8)(byte - borrow),  borrow = [previous sample at this (channel, index) >= 0], 1 before the first frame.
+// `state` carries the borrow per (index in block, channel) from call to call.
+void zf_wav8_state_init(uint8_t *state, size_t n) { memset(state, 1, n); }
+
+void zf_wav8_to_samples(const uint8_t *raw, uint64_t samples_per_channel, uint32_t channels, uint32_t block_size,
+                        uint64_t first_sample, uint8_t *state, int8_t *out) {
+    const uint64_t total = samples_per_channel * channels;
+    const uint64_t period = (uint64_t)block_size * channels;
+    uint64_t s = (first_sample % block_size) * channels;  // position inside the block's state
+    for (uint64_t k = 0; k < total; k++) {
+        const int8_t v = (int8_t)(uint8_t)(raw[k] - state[s]);
+        out[k] = v;
+        state[s] = v >= 0 ? 1 : 0;
+        if (++s == period) s = 0;
+    }
+}
+
+// ---- optional libcrypto MD5 (md5.zig:3-35: `-Dlink_ossl` swaps std.crypto's MD5 for OpenSSL's) ------------------------
+}  // extern "C"
+
+#include <dlfcn.h>
+
+#include <initializer_list>
+namespace {
+typedef int (*ossl_init_t)(void *);
+typedef int (*ossl_update_t)(void *, const void *, size_t);
+typedef int (*ossl_final_t)(unsigned char *, void *);
+ossl_init_t g_ossl_init = nullptr;
+ossl_update_t g_ossl_update = nullptr;
+ossl_final_t g_ossl_final = nullptr;
+}  // namespace
+extern "C" {
+
+int zf_md5_openssl_available(void) {
+    static int state = -1;
+    if (state >= 0) return state;
+    void *h = nullptr;
+    for (const char *name : {"libcrypto.so.3", "libcrypto.so.1.1", "libcrypto.so"}) {
+        h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (h) break;
+    }
+    if (h) {
+        g_ossl_init = (ossl_init_t)dlsym(h, "MD5_Init");      // md5.zig:33-35
+        g_ossl_update = (ossl_update_t)dlsym(h, "MD5_Update");
+        g_ossl_final = (ossl_final_t)dlsym(h, "MD5_Final");
+    }
+    state = (g_ossl_init && g_ossl_update && g_ossl_final) ? 1 : 0;
+    return state;
+}
+
+// One-shot interface over either implementation; ctx must hold 128 bytes (OpenSSL's MD5_CTX has 92, md5.zig:5-13).
+int zf_md5x_init(void *ctx, int use_openssl) {
+    if (use_openssl && zf_md5_openssl_available()) {
+        g_ossl_init(ctx);
+        return 1;
+    }
+    zf_md5_init((zf_md5 *)ctx);
+    return 0;
+}
+void zf_md5x_update(void *ctx, int ossl, const uint8_t *data, size_t len) {
+    if (ossl) g_ossl_update(ctx, data, len);
+    else zf_md5_update((zf_md5 *)ctx, data, len);
+}
+void zf_md5x_final(void *ctx, int ossl, uint8_t digest[16]) {
+    if (ossl) g_ossl_final(digest, ctx);
+    else zf_md5_final((zf_md5 *)ctx, digest);
+}
+
 // ---- WavReader.getFmt, wav_reader.zig:116-170 -----------------------------------------------------------------
 
 static inline uint32_t le32(const uint8_t *p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24; }

@@ -68,6 +68,8 @@ struct FrameJob {
     uint32_t max_rice_order;
     uint32_t max_rice_param;
     uint32_t use_tma;
+    uint32_t bit_depth;            // general kernels: sample depth when it is not the container's (8-bit samples travel in
+                                   // 16-bit containers); 0 = 8 x container bytes
     uint32_t pdl_trigger;          // general kernels: release the dependent launch at once (the one-CTA last-frame
                                    // launch in front of the persistent full-frame kernel)
 };
@@ -1088,7 +1090,7 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_kernel(const Fra
     SmemCommon &c = sm.c;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t n = FULL ? (uint32_t)kMaxBlock : job.block_size;
-    const uint32_t depth = 8u * BYTES;
+    const uint32_t depth = job.bit_depth ? job.bit_depth : 8u * BYTES;
     const uint32_t frame_bytes = n * 2u * BYTES;
     const uint32_t base = (uint32_t)t * kSpt;
     const bool tma = FULL && job.use_tma;
@@ -1266,6 +1268,14 @@ __global__ void zf_append_tail_kernel(const uint8_t *tail, const uint32_t *tail_
         frame_sizes[fidx] = size;
         *total = off + size;
     }
+}
+
+// 8-bit samples (signed, one byte each, as WavReader.fillSamples leaves them -- wav_reader.zig:71-88) -> 16-bit little-endian
+// containers, so that the 16-bit kernels encode them with depth 8
+__global__ void zf_widen8_kernel(const int8_t *in, int16_t *out, unsigned long long n) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        out[i] = (int16_t)in[i];
 }
 
 }  // namespace zf

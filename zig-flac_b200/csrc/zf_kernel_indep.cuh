@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_indep_kernel(const Fram
     if (job.pdl_trigger) pdl_launch_dependents();
     const uint32_t n = job.block_size;
     const uint32_t nch = job.channels;
-    const uint32_t depth = 8u * BYTES;
+    const uint32_t depth = job.bit_depth ? job.bit_depth : 8u * BYTES;
     const uint32_t base = (uint32_t)t * kSpt;
     const uint32_t bit_words = indep_bit_words(BYTES, (int)nch);
 
