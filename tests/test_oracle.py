@@ -138,8 +138,11 @@ def test_wav_parser_and_exit_codes(oracle, zf):
         assert rc == 0 and oracle.decode(flac)["rc"] == 0
     assert oracle.wav_to_flac(b"RIFX" + bytes(60))[0] == -1          # NotRiffFile
     assert oracle.wav_to_flac(b"RIFF\0\0\0\0WAVX" + bytes(60))[0] == -2  # NotWaveFile
-    wav8 = oracle.make_wav(bytes(200), 2, 8, 8000)
-    assert oracle.wav_to_flac(wav8)[0] == 2                           # unsupported by this FLAC encoder
+    rc8, flac8 = oracle.wav_to_flac(oracle.make_wav(bytes(200), 2, 8, 8000))   # 8-bit: accepted (wav_reader.zig:71-78)
+    assert rc8 == 0 and oracle.decode(flac8)["rc"] == 0 and oracle.decode(flac8)["streaminfo"].bits == 8
+    wav12 = oracle.make_wav(bytes(400), 2, 16, 8000)
+    wav12 = wav12[:34] + (12).to_bytes(2, "little") + wav12[36:]      # 12 valid bits in 2-byte containers
+    assert oracle.wav_to_flac(wav12)[0] == 2                          # frame_writer.zig:221-233 has no code for it
 
 
 def test_independent_channels_round_trip(oracle):
