@@ -28,12 +28,16 @@ WORKLOADS = {
     "c1_16bit_44k1_60s": (16, 44100, 60),
     "c2_24bit_96k_600s": (24, 96000, 600),
     "c3_32bit_192k_600s": (32, 192000, 600),
+    # BASELINE config 4: config 1's stream with LPC subframes up to order 12 (the reference has no LPC: the CPU arm is the
+    # oracle's statement of the same LPC specification, zigflac_lpc.h)
+    "c4_16bit_44k1_60s_lpc12": (16, 44100, 60),
     # BASELINE config 5: the 10-hour stream in eight contiguous frame-range shards; one shard (75 min, 2.6 GB of PCM)
     # per GPU, so `--gpus 8` under torchrun is the whole stream
     "c5_24bit_96k_10h_shard8": (24, 96000, 4500),
     # not a BASELINE config: config 1's format at bandwidth-config length (development aid)
     "x1_16bit_44k1_3600s": (16, 44100, 3600),
 }
+LPC_ORDER = {"c4_16bit_44k1_60s_lpc12": 12}
 DEFAULT_WORKLOAD = "c2_24bit_96k_600s"
 BLOCK = 4096
 CHANNELS = 2
@@ -155,7 +159,8 @@ def make_config(workload, world):
     pcm_bytes = nsamples * CHANNELS * bits // 8
     resident = pcm_bytes < 2 * L2_BYTES
     return {"workload": workload, "bit_depth": bits, "sample_rate": rate, "channels": CHANNELS,
-            "block_size": BLOCK, "prediction": "fixed", "stereo_decorrelation": True, "max_rice_order": 8,
+            "block_size": BLOCK, "prediction": ("lpc<=%d + fixed" % LPC_ORDER[workload]) if workload in LPC_ORDER else "fixed",
+            "stereo_decorrelation": True, "max_rice_order": 8,
             "max_rice_param": 30, "seconds_per_gpu": seconds, "frames_per_gpu": nframes,
             "parallelism": f"frame-range shards x{world}, no collective",
             "l2_resident": resident, "l2_flush": resident,
@@ -185,7 +190,7 @@ def run_reference(args, rank, world):
     sample_seconds = min(seconds, 60 if bits == 16 else 30)
     n = (rate * sample_seconds // BLOCK) * BLOCK
     pcm = oracle_lib.synth_pcm(n, rate, bits)
-    cfg = oracle_lib.config(CHANNELS, bits)
+    cfg = oracle_lib.config(CHANNELS, bits, lpc_order=LPC_ORDER.get(args.workload, 0))
     warmup = max(args.warmup, 1)
     for _ in range(warmup):
         oracle_lib.encode_pcm(pcm, n, cfg, rate, threads=cores)
@@ -247,8 +252,8 @@ def main():
     zf.synth_pcm(nsamples, rate, bits, first_sample=s0, threads=threads, out=h_pcm.numpy())
     d_pcm = h_pcm.to(dev, non_blocking=True)
 
-    enc = zf.Encoder(zf.Config.default(CHANNELS, bits), rate, device_id=local_rank,
-                     max_frames_per_batch=max(nframes, 1))
+    enc_cfg = zf.Config(CHANNELS, bits, lpc_order=LPC_ORDER.get(args.workload, 0))
+    enc = zf.Encoder(enc_cfg, rate, device_id=local_rank, max_frames_per_batch=max(nframes, 1))
     out_cap = enc.max_batch_bytes(nframes)
     d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
     d_sizes = torch.zeros(max(nframes, 1), dtype=torch.int32, device=dev)
@@ -316,7 +321,7 @@ def main():
 
     # ---- end to end through the C ABI with pinned host buffers (H2D + encode + D2H every step) ----
     e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
-    enc2 = zf.Encoder(zf.Config.default(CHANNELS, bits), rate, device_id=local_rank, max_frames_per_batch=2048)
+    enc2 = zf.Encoder(enc_cfg, rate, device_id=local_rank, max_frames_per_batch=2048)
     h_out = torch.empty(out_cap, dtype=torch.uint8, pin_memory=True)
     h_out_np = h_out.numpy()
     h_pcm_np = h_pcm.numpy()
@@ -406,7 +411,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
                          "traffic_source": (ncu or {}).get("file"), "issue": issue,
-                         "kernel": ("zf::v3::zf_encode_stereo_v3_kernel<%d>" % (bits // 8)) if not os.environ.get("ZF_LEGACY_KERNEL") else ("zf::zf_encode_stereo_full_kernel<%d>" % (bits // 8)),
+                         "kernel": ("zf::lpc::zf_encode_stereo_lpc_kernel<%d>" % (bits // 8)) if args.workload in LPC_ORDER else ("zf::v3::zf_encode_stereo_v3_kernel<%d>" % (bits // 8)) if not os.environ.get("ZF_LEGACY_KERNEL") else ("zf::zf_encode_stereo_full_kernel<%d>" % (bits // 8)),
                          "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": kernel_bytes,
                          "peak_source": peak_src,
                          "note": "bound is nominal: the kernel is integer-issue bound (see `issue`), HBM is mostly idle; DESIGN.md section 4"},
@@ -415,9 +420,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib
-            sample_seconds = 120
+            sample_seconds = min(120, seconds)
             n = (rate * sample_seconds // BLOCK) * BLOCK
-            cfg = oracle_lib.config(CHANNELS, bits)
+            cfg = oracle_lib.config(CHANNELS, bits, lpc_order=LPC_ORDER.get(args.workload, 0))
             sample = h_pcm_np[: n * ic_bytes]
             t0 = time.perf_counter()
             ref, ref_sizes = oracle_lib.encode_pcm(sample, n, cfg, rate, threads=1)

@@ -60,7 +60,11 @@ typedef struct zf_config {
     uint8_t stereo_decorrelation;  /* Feature.stereo_decorrelation */
     uint8_t max_rice_order;        /* Feature.max_rice_order, 0..8 */
     uint8_t max_rice_param;        /* Feature.max_rice_param, 1..30 */
-    uint8_t reserved0;
+    uint8_t lpc_order;             /* 0 = the reference's encoder (fixed predictors only).  1..12: LPC subframes as one more
+                                      candidate per channel, up to this order (BASELINE config 4).  The reference has no
+                                      LPC (encoder.zig:626-640 is a stub), so this mode has no byte-parity claim: the
+                                      stream is standard FLAC, decodes losslessly and is not larger than the FIXED one.
+                                      Stereo with decorrelation, 8/16/24-bit only. */
     int32_t device_id;             /* CUDA device ordinal */
     uint32_t max_frames_per_batch; /* capacity of one submit; device buffers are sized from it */
 } zf_config;

@@ -10,6 +10,7 @@
  */
 #include "zigflac_oracle.h"
 
+#include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -187,6 +188,7 @@ struct zo_encoder {
     int64_t *samples64;
     uint64_t rice_sum_buf[ZO_MAX_RICE_ORDER + 1][ZO_MAX_PART];
     uint64_t rice_max_buf[ZO_MAX_RICE_ORDER + 1][ZO_MAX_PART];
+    int32_t *lpc_tmp; /* LPC extension: residuals of the candidate being tried */
 };
 
 void zo_config_default(zo_config *cfg, uint8_t channels, uint8_t bit_depth) { /* encoder.zig:642-655 */
@@ -196,7 +198,7 @@ void zo_config_default(zo_config *cfg, uint8_t channels, uint8_t bit_depth) { /*
     cfg->stereo_decorrelation = 1;
     cfg->max_rice_order = 8;
     cfg->max_rice_param = 30; /* rice.MAX_PARAM = MAX_PARAM_5BIT = 31 - 1, rice.zig:9-10 */
-    cfg->reserved = 0;
+    cfg->lpc_order = 0;
 }
 
 size_t zo_max_frame_bytes(uint16_t block_size, uint8_t bit_depth, uint8_t channels, int stereo_decorrelation) {
@@ -233,7 +235,8 @@ zo_encoder *zo_encoder_create(const zo_config *cfg) { /* encoder.zig:44-118 */
         e->sample64_store = (int64_t *)calloc(ZO_GUARD + block_len + ZO_GUARD, 8);
         e->samples64 = e->sample64_store + ZO_GUARD;
     }
-    if (!e->fwriter_buf || !e->sample_store || !e->residual_store) {
+    e->lpc_tmp = (int32_t *)calloc(block_len + ZO_GUARD, 4);
+    if (!e->fwriter_buf || !e->sample_store || !e->residual_store || !e->lpc_tmp) {
         zo_encoder_destroy(e);
         return NULL;
     }
@@ -246,6 +249,7 @@ void zo_encoder_destroy(zo_encoder *e) { /* encoder.zig:121-164 */
     free(e->sample_store);
     free(e->residual_store);
     free(e->sample64_store);
+    free(e->lpc_tmp);
     free(e);
 }
 
@@ -459,6 +463,8 @@ static uint64_t rice_calc_params(zo_encoder *e, const int32_t *residuals, size_t
     return optimal_bit_count;
 }
 
+#include "zigflac_lpc.h" /* LPC extension (no reference counterpart); inert while zo_config.lpc_order == 0 */
+
 /* ------------------------------------------------------------------------------------------ */
 /* encoder.zig: calcWasteBits, chooseSubframeEncoding, processChannels                          */
 /* ------------------------------------------------------------------------------------------ */
@@ -528,6 +534,29 @@ static uint64_t choose_subframe_encoding(zo_encoder *e, int wide, int32_t *s32, 
         enc->residuals = residuals_dst;
         enc->rice = rice_config;
         for (int i = 0; i < 4; i++) enc->warmup[i] = wide ? s64[i] : (int64_t)s32[i]; /* :545-549 */
+        enc->est_bits = bit_size;
+    }
+    if (e->config.lpc_order > 0) { /* extension, zigflac_lpc.h step 8; never reached on the reference's path */
+        uint64_t cost = (enc->kind == ZO_FIXED) ? bit_size + (uint64_t)enc->order * bps : bit_size;
+        zl_model m;
+        if (zl_analyse(wide ? NULL : s32, wide ? s64 : NULL, len, bps, e->config.lpc_order, e->lpc_tmp, &m)) {
+            zo_rice_config rc;
+            const uint64_t lpc_bits = rice_calc_params(e, e->lpc_tmp, len, e->config.max_rice_order,
+                                                       e->config.max_rice_param, bps, m.order, &rc);
+            const uint64_t lpc_cost = lpc_bits + (uint64_t)m.order * (bps + m.precision) + 9;
+            if (lpc_bits < (uint64_t)len * bps && lpc_cost < cost) { /* the residual must beat VERBATIM by itself */
+                cost = lpc_cost;
+                enc->kind = ZO_LPC;
+                enc->order = (uint8_t)m.order;
+                enc->lpc_shift = (uint8_t)m.shift;
+                enc->lpc_precision = (uint8_t)m.precision;
+                memcpy(enc->lpc_q, m.q, sizeof m.q);
+                memcpy(residuals_dst, e->lpc_tmp, len * sizeof(int32_t));
+                enc->residuals = residuals_dst;
+                enc->rice = rc;
+            }
+        }
+        bit_size = cost;
         enc->est_bits = bit_size;
     }
     return bit_size;
@@ -847,6 +876,43 @@ static void write_fixed_subframe(fwriter *w, const int64_t warmup[4], const int3
     }
 }
 
+/* LPC extension (zigflac_lpc.h; FLAC format: SUBFRAME_LPC): header 1xxxxx with order - 1, warm-ups, 4-bit precision - 1,
+ * 5-bit shift, the quantised coefficients, then the residual coded exactly like a FIXED subframe's. */
+static void write_lpc_subframe(fwriter *w, const zo_encoding *enc, unsigned bps) {
+    const zo_rice_config *rc = &enc->rice;
+    const unsigned order = enc->order, waste_bits = enc->waste_bits;
+    const size_t len = enc->len;
+    const unsigned param_len = rc->method + 4u;
+    const size_t part_count = (size_t)1 << rc->part_order;
+    write_bits(w, 8, ((0x20u | (order - 1)) << 1) | (waste_bits ? 1u : 0u));
+    if (waste_bits) write_bits(w, waste_bits, 1);
+    for (unsigned i = 0; i < order; i++)
+        write_bits_signed(w, bps, (uint64_t)(enc->wide ? enc->samples64[i] : (int64_t)enc->samples32[i]));
+    write_bits(w, 4, enc->lpc_precision - 1u);
+    write_bits(w, 5, enc->lpc_shift);
+    for (unsigned i = 0; i < order; i++) write_bits_signed(w, enc->lpc_precision, (uint64_t)(int64_t)enc->lpc_q[i]);
+    write_bits(w, 2 + 4, ((unsigned)rc->method << 4) | rc->part_order);
+    const int32_t *remain_residuals = enc->residuals + order;
+    size_t part_len = (len >> rc->part_order) - order;
+    for (size_t p = 0; p < part_count; p++) {
+        const uint8_t param = rc->params[p];
+        const int32_t *part_residuals = remain_residuals;
+        const size_t this_len = part_len;
+        remain_residuals += part_len;
+        part_len = len >> rc->part_order;
+        if (param & 0x80) {
+            const unsigned esc_bits = param & 0x7f;
+            write_bits(w, param_len, 0xF | ((unsigned)rc->method << 4));
+            write_bits(w, 5, esc_bits);
+            if (esc_bits == 0) continue;
+            for (size_t i = 0; i < this_len; i++) write_bits_signed(w, esc_bits, (uint64_t)(uint32_t)part_residuals[i]);
+            continue;
+        }
+        write_bits(w, param_len, param);
+        write_rice_part(w, part_residuals, this_len, param);
+    }
+}
+
 /* encoder.zig:287-310 */
 static void write_channel_subframe(fwriter *w, const zo_encoding *enc, unsigned bit_depth) {
     const unsigned bps = bit_depth - enc->waste_bits;
@@ -855,6 +921,7 @@ static void write_channel_subframe(fwriter *w, const zo_encoding *enc, unsigned 
         case ZO_VERBATIM:
             write_verbatim_subframe(w, enc->wide, enc->samples32, enc->samples64, enc->len, bps, enc->waste_bits);
             break;
+        case ZO_LPC: write_lpc_subframe(w, enc, bps); break;
         default:
             write_fixed_subframe(w, enc->warmup, enc->residuals, enc->len, enc->order, &enc->rice, bps, enc->waste_bits);
     }

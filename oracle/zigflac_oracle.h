@@ -34,7 +34,7 @@ typedef struct {
     uint8_t stereo_decorrelation;
     uint8_t max_rice_order;
     uint8_t max_rice_param;
-    uint8_t reserved;
+    uint8_t lpc_order; /* 0 = the reference's path (fixed predictors only); 1..32 = LPC extension, zigflac_lpc.h */
 } zo_config;
 
 /* FrameInfo, encoder.zig:658-663 */
@@ -52,7 +52,7 @@ typedef struct {
     uint8_t params[ZO_MAX_PART];
 } zo_rice_config;
 
-enum { ZO_CONSTANT = 0, ZO_VERBATIM = 1, ZO_FIXED = 2 };
+enum { ZO_CONSTANT = 0, ZO_VERBATIM = 1, ZO_FIXED = 2, ZO_LPC = 3 /* extension: zigflac_lpc.h */ };
 
 /* SubframeType.Encoding, encoder.zig:678-702, flattened; also the per-subframe decision record
  * tests diff against the GPU path. */
@@ -69,6 +69,8 @@ typedef struct {
     const int32_t *residuals;
     uint32_t len;
     zo_rice_config rice;
+    uint8_t lpc_shift, lpc_precision; /* ZO_LPC: order in `order`, warm-ups read from the plane */
+    int32_t lpc_q[32];
 } zo_encoding;
 
 typedef struct {

@@ -9,12 +9,13 @@
 #define ZF_HOST_EMU 1
 #include "cuda_emu.h"
 
-namespace zf { alignas(128) unsigned char zf_smem[256 * 1024]; namespace v3 { alignas(128) unsigned char zf_smem[256 * 1024]; } }
+namespace zf { alignas(128) unsigned char zf_smem[256 * 1024]; namespace v3 { alignas(128) unsigned char zf_smem[256 * 1024]; } namespace lpc { alignas(128) unsigned char zf_smem[256 * 1024]; } }
 
 #include "../../zig-flac_b200/csrc/zf_kernel.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_indep.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_full.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_v3.cuh"
+#include "../../zig-flac_b200/csrc/zf_kernel_lpc.cuh"
 
 namespace emu {
 emu_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
@@ -112,9 +113,25 @@ static zf::FrameJob g_job;
 static int g_bytes, g_full, g_indep, g_v3;
 static int g_allow_v3 = 1;
 static unsigned g_bit_depth = 0;  // 0 = 8 x container bytes
+static unsigned g_lpc_order = 0;
+static std::vector<uint16_t> g_win;
+static void make_window(uint32_t n) {  // zf-LPC v1 window, as zf_capi.cu computes it
+    g_win.assign(n, 16384);
+    if (n <= 1) return;
+    const unsigned long long den = (unsigned long long)(n - 1) * (n - 1);
+    for (uint32_t i = 0; i < n; i++) {
+        const long long d = 2ll * i - (long long)(n - 1);
+        g_win[i] = (uint16_t)(16384u - (uint32_t)((((unsigned long long)(d * d)) << 14) / den));
+    }
+}
 static unsigned long long g_v3_frames = 0;
 
 static void kernel_entry(void *) {
+    if (g_lpc_order && !g_indep) {
+        if (g_bytes == 2) zf::lpc::zf_encode_stereo_lpc_kernel<2>(g_job);
+        else zf::lpc::zf_encode_stereo_lpc_kernel<3>(g_job);
+        return;
+    }
     if (g_indep) {
         if (g_bytes == 2) zf::zf_encode_indep_kernel<2>(g_job);
         else if (g_bytes == 3) zf::zf_encode_indep_kernel<3>(g_job);
@@ -175,10 +192,12 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     j.frame_stride = block_size * channels * bytes_per_sample; j.sample_rate = sample_rate; j.channels = channels;
     j.max_rice_order = max_rice_order; j.max_rice_param = max_rice_param; j.use_tma = 1;
     j.bit_depth = g_bit_depth;
+    j.lpc_order = g_lpc_order;
     g_bytes = bytes_per_sample;
     if (full) {
         j.pcm = pcm; j.n_frames = (uint32_t)full; j.frame_base = 0; j.block_size = block_size;
-        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8 && g_bit_depth == 0;
+        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8 && g_bit_depth == 0 && !g_lpc_order;
+        if (g_lpc_order) { make_window(block_size); j.lpc_window = g_win.data(); }
         bool table = false;
         for (unsigned r : {88200u, 176400u, 192000u, 8000u, 16000u, 22050u, 24000u, 32000u, 44100u, 48000u, 96000u}) table |= r == sample_rate;
         g_v3 = g_full && g_allow_v3 && max_rice_param == 30 && table && g_bit_depth == 0;
@@ -192,6 +211,7 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     }
     if (tail) {
         j.pcm = pcm + full * j.frame_stride; j.n_frames = 1; j.frame_base = (uint32_t)full; j.block_size = tail;
+        if (g_lpc_order) { make_window(tail); j.lpc_window = g_win.data(); }
         g_full = 0;
         g_job = j;
         ticket = 0;
@@ -204,6 +224,7 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
 
 void emu_allow_v3(int on) { g_allow_v3 = on; }
 void emu_set_bit_depth(unsigned d) { g_bit_depth = d; }
+void emu_set_lpc_order(unsigned o) { g_lpc_order = o; }
 unsigned long long emu_v3_frames(void) { return g_v3_frames; }
 unsigned long long emu_v3_wide_frames(void) { return zf::v3::g_emu_wide_frames; }
 unsigned long long emu_v3_narrow_frames(void) { return zf::v3::g_emu_narrow_frames; }

@@ -17,7 +17,7 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "_ref", "libzigflac_oracle.so")
 class ZoConfig(C.Structure):
     _fields_ = [("block_size", C.c_uint16), ("bit_depth", C.c_uint8), ("channels", C.c_uint8),
                 ("stereo_decorrelation", C.c_uint8), ("max_rice_order", C.c_uint8),
-                ("max_rice_param", C.c_uint8), ("reserved", C.c_uint8)]
+                ("max_rice_param", C.c_uint8), ("lpc_order", C.c_uint8)]
 
 
 class ZoFrameInfo(C.Structure):
@@ -67,7 +67,7 @@ _lib = None
 def build(force=False):
     """Compile the oracle with its committed Makefile (outputs only into oracle/_ref/)."""
     srcs = [os.path.join(ORACLE_DIR, f) for f in ("zigflac_oracle.c", "flac_decode.c", "zigflac_oracle.h",
-                                                  "oracle_cli.c", "Makefile")]
+                                                  "oracle_cli.c", "Makefile", "zigflac_lpc.h")]
     srcs.append(os.path.join(ROOT, "zig-flac_b200", "csrc", "zf_synth.c"))
     stale = force or not os.path.exists(ORACLE_SO) or any(
         os.path.getmtime(s) > os.path.getmtime(ORACLE_SO) for s in srcs)
@@ -147,13 +147,15 @@ def _buf(b):
     return np.ascontiguousarray(a)
 
 
-def config(channels=2, bit_depth=16, block_size=4096, stereo_decorrelation=1, max_rice_order=8, max_rice_param=30):
+def config(channels=2, bit_depth=16, block_size=4096, stereo_decorrelation=1, max_rice_order=8, max_rice_param=30,
+           lpc_order=0):
     cfg = ZoConfig()
     lib().zo_config_default(C.byref(cfg), channels, bit_depth)
     cfg.block_size = block_size
     cfg.stereo_decorrelation = stereo_decorrelation
     cfg.max_rice_order = max_rice_order
     cfg.max_rice_param = max_rice_param
+    cfg.lpc_order = lpc_order  # 0 = the reference's path; > 0 = LPC extension (oracle/zigflac_lpc.h)
     return cfg
 
 

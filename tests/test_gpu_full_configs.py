@@ -231,3 +231,48 @@ def test_8bit_wav(zf, oracle, channels):
     with zf.Encoder(zf.Config.default(channels, 8), 22050, max_frames_per_batch=7) as enc:
         g, gs = enc.encode_pcm(signed, n, 0)
     assert np.array_equal(gs, fs) and g.tobytes() == fr.tobytes()
+
+
+@pytest.mark.parametrize("bits,rate,seconds", [(16, 44100, 60), (24, 96000, 12)])
+def test_lpc_extension_config4(zf, oracle, bits, rate, seconds):
+    """BASELINE config 4 (16-bit / 44.1 kHz, LPC order <= 12 with quantised coefficients).  The reference has no LPC
+    (encoder.zig:626-640 is a stub), so the bar is: (1) the GPU stream is bit-identical to the CPU statement of the
+    same specification (oracle/zigflac_lpc.h); (2) the independent decoder returns the PCM; (3) the stream is not
+    larger than the reference's FIXED-only stream."""
+    n = rate * seconds
+    pcm = zf.synth_pcm(n, rate, bits)
+    with zf.Encoder(zf.Config(2, bits, lpc_order=12), rate, max_frames_per_batch=512) as enc:
+        got, sizes = enc.encode_pcm(pcm, n, 0)
+    ref, ref_sizes = oracle.encode_pcm(pcm, n, oracle.config(2, bits, lpc_order=12), rate, 0, threads=os.cpu_count() or 1)
+    _compare_stream(got, sizes, ref, ref_sizes, f"lpc {bits}-bit")
+    d = oracle.decode(oracle.wrap_frames(got, 2, bits, rate, total_samples=n), max_frames=1 << 15)
+    assert d["rc"] == 0 and d["n_frames"] == sizes.size
+    raw = np.frombuffer(pcm, dtype=np.uint8).reshape(-1, bits // 8).astype(np.int32)
+    expect = sum(raw[:, k] << (8 * k) for k in range(bits // 8))
+    expect = (expect ^ (1 << (bits - 1))) - (1 << (bits - 1))
+    assert np.array_equal(d["pcm"], expect)
+    assert sum(1 for f in d["frames"] for s in f.sub[:2] if s.type == 3) > sizes.size  # mostly LPC subframes
+    fixed, _ = oracle.encode_pcm(pcm, n, oracle.config(2, bits), rate, 0, threads=os.cpu_count() or 1)
+    assert got.size < fixed.size, (got.size, fixed.size)
+    # outside the extension's scope: refused, not silently encoded some other way
+    for bad in (dict(channels=1, bits=16, lpc_order=12), dict(channels=2, bits=32, lpc_order=12),
+                dict(channels=2, bits=16, lpc_order=13), dict(channels=2, bits=16, lpc_order=4, stereo_decorrelation=False)):
+        kw = dict(bad)
+        ch, b = kw.pop("channels"), kw.pop("bits")
+        with pytest.raises(zf.FlacGpuError):
+            zf.Encoder(zf.Config(ch, b, **kw), rate)
+
+
+def test_lpc_input_classes(zf, oracle):
+    """Every stereo input class through the LPC kernel: GPU == CPU statement, lossless."""
+    import signals
+    for bits in (16, 24):
+        with zf.Encoder(zf.Config(2, bits, lpc_order=12), 48000, max_frames_per_batch=8) as enc:
+            for name, L, R in signals.stereo_classes(bits):
+                pcm = oracle.pcm_bytes_from_int(signals.interleave([L, R]), bits)
+                ref, rs = oracle.encode_pcm(pcm, L.size, oracle.config(2, bits, lpc_order=12), 48000, 0)
+                got, gs = enc.encode_pcm(pcm, L.size, 0)
+                assert np.array_equal(rs, gs), (name, bits)
+                assert ref.tobytes() == got.tobytes(), (name, bits)
+                d = oracle.decode(oracle.wrap_frames(got, 2, bits, 48000))
+                assert d["rc"] == 0 and np.array_equal(d["pcm"], signals.interleave([L, R])), (name, bits)

@@ -23,10 +23,10 @@ CSRC = os.path.join(os.path.dirname(HERE), "zig-flac_b200", "csrc")
 @pytest.fixture(scope="module")
 def emu():
     srcs = [os.path.join(EMU_DIR, f) for f in ("emu_main.cpp", "cuda_emu.h")] + [
-        os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_kernel_full.cuh", "zf_kernel_v3.cuh", "zf_dev.h")]
+        os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_kernel_full.cuh", "zf_kernel_v3.cuh", "zf_kernel_lpc.cuh", "zf_dev.h")]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
         os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", EMU_SO,
+        subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", EMU_SO,
                         os.path.join(EMU_DIR, "emu_main.cpp")], check=True)
     lib = C.CDLL(EMU_SO)
     lib.emu_encode.restype = C.c_longlong
@@ -234,3 +234,45 @@ def test_8bit_samples_through_the_16bit_kernels(emu, oracle):
             assert ref.tobytes() == got.tobytes()
     finally:
         emu.emu_set_bit_depth(0)
+
+
+@pytest.mark.parametrize("bits", [16, 24])
+def test_lpc_kernel_logic(emu, oracle, bits):
+    """LPC extension (zf_kernel_lpc.cuh; the reference has none, encoder.zig:626-640): the kernel's integer window /
+    autocorrelation, double-precision Levinson-Durbin, order choice, quantisation, residual and the choice against the
+    FIXED candidate, bit for bit against the CPU statement of the same specification (oracle/zigflac_lpc.h), and the
+    stream through the independent decoder."""
+    import zigflac_b200 as zf
+    emu.emu_set_lpc_order.argtypes = [C.c_uint]
+    rate = 44100 if bits == 16 else 96000
+    rng = np.random.default_rng(bits)
+    F = 1 << (bits - 1)
+    streams = []
+    n = 2 * 4096 + 1500
+    streams.append(("synthetic", zf.synth_pcm(n, rate, bits), n))
+    t = np.arange(n)
+    L = (0.3 * F * np.sin(t * 0.3) + 0.2 * F * np.sin(t * 0.71 + 1) + rng.normal(0, F / 500, n)).astype(np.int64)
+    R = (0.25 * F * np.sin(t * 0.3 + 0.4) + rng.normal(0, F / 300, n)).astype(np.int64)
+    streams.append(("tones", oracle.pcm_bytes_from_int(signals.interleave([L, R]), bits), n))
+    for name, a, b in signals.stereo_classes(bits, n=4096 + 900):
+        streams.append((name, oracle.pcm_bytes_from_int(signals.interleave([a, b]), bits), a.size))
+    m = 100  # short frames: below 64 samples LPC is off, above it runs on the short geometry
+    for k in (5, 63, 64, 100, 1000):
+        x = (0.2 * F * np.sin(np.arange(k) * 0.2)).astype(np.int64) + rng.integers(-9, 10, k)
+        streams.append((f"short{k}", oracle.pcm_bytes_from_int(signals.interleave([x, x // 3]), bits), k))
+    n_lpc = 0
+    try:
+        emu.emu_set_lpc_order(12)
+        for name, pcm, ns in streams:
+            ref, rs = oracle.encode_pcm(pcm, ns, oracle.config(2, bits, lpc_order=12), rate, 0)
+            got, gs = _emu_encode(emu, pcm, ns, bits, rate=rate)
+            assert np.array_equal(rs, gs), name
+            assert ref.tobytes() == got.tobytes(), name
+            d = oracle.decode(oracle.wrap_frames(got, 2, bits, rate))
+            assert d["rc"] == 0, name
+            n_lpc += sum(1 for f in d["frames"] for s in f.sub[:2] if s.type == 3)
+            fixed, _ = oracle.encode_pcm(pcm, ns, oracle.config(2, bits), rate, 0)
+            assert got.size <= fixed.size + 8 * len(d["frames"]), name  # never worse than FIXED beyond rounding per frame
+    finally:
+        emu.emu_set_lpc_order(0)
+    assert n_lpc > 10  # LPC subframes really were chosen and written

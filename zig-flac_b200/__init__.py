@@ -41,7 +41,7 @@ class FlacGpuError(RuntimeError):
 class ZfConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("block_size", C.c_uint16), ("bit_depth", C.c_uint8),
                 ("channels", C.c_uint8), ("sample_rate", C.c_uint32), ("stereo_decorrelation", C.c_uint8),
-                ("max_rice_order", C.c_uint8), ("max_rice_param", C.c_uint8), ("reserved0", C.c_uint8),
+                ("max_rice_order", C.c_uint8), ("max_rice_param", C.c_uint8), ("lpc_order", C.c_uint8),
                 ("device_id", C.c_int32), ("max_frames_per_batch", C.c_uint32)]
 
 
@@ -153,13 +153,14 @@ class Config:
     """Encoder.Config (encoder.zig:609-656); `default` is Config.default(channels, bit_depth) (:642-655)."""
 
     def __init__(self, channels, bit_depth, block_size=4096, stereo_decorrelation=True, max_rice_order=8,
-                 max_rice_param=30):
+                 max_rice_param=30, lpc_order=0):
         self.channels = channels
         self.bit_depth = bit_depth
         self.block_size = block_size
         self.stereo_decorrelation = stereo_decorrelation
         self.max_rice_order = max_rice_order
         self.max_rice_param = max_rice_param
+        self.lpc_order = lpc_order  # 0 = the reference's encoder; 1..12 = LPC extension (no reference counterpart)
 
     @staticmethod
     def default(channels, bit_depth):
@@ -172,6 +173,7 @@ class Config:
         c.stereo_decorrelation = 1 if self.stereo_decorrelation else 0
         c.max_rice_order = self.max_rice_order
         c.max_rice_param = self.max_rice_param
+        c.lpc_order = self.lpc_order
         c.device_id = device_id
         c.max_frames_per_batch = max_frames_per_batch
         return c

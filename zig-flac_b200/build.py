@@ -54,7 +54,9 @@ def build(force=False, verbose=False):
             # -ffp-contract=off: the generator must round identically wherever it is built
             cmd = ["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-c", "-o", obj, src]
         else:
-            cmd = [NVCC, "-O3", "-std=c++17", "-lineinfo"] + ARCH + ["-Xcompiler", "-fPIC,-pthread", "-c", "-o", obj, src]
+            # -fmad=false: the LPC extension's double arithmetic is one IEEE rounding per operation (zf_kernel_lpc.cuh); nothing
+            # else in the kernels is floating point
+            cmd = [NVCC, "-O3", "-std=c++17", "-lineinfo", "-fmad=false"] + ARCH + ["-Xcompiler", "-fPIC,-pthread", "-c", "-o", obj, src]
             if verbose and f.endswith(".cu"):
                 cmd[1:1] = ["-Xptxas", "-v"]
         subprocess.run(cmd, check=True)

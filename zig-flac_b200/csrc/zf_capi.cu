@@ -19,6 +19,7 @@
 #include "zf_kernel_indep.cuh"
 #include "zf_kernel_full.cuh"
 #include "zf_kernel_v3.cuh"
+#include "zf_kernel_lpc.cuh"
 
 namespace {
 
@@ -54,6 +55,8 @@ struct Slot {  // one in-flight batch: device buffers + pinned staging
     unsigned long long *d_total = nullptr;
     unsigned long long *h_total = nullptr;  // pinned: [0] total, [1] status
     cudaStream_t stream = nullptr;
+    uint16_t *d_win_tail = nullptr;          // LPC: window of the short last frame
+    uint32_t win_tail_len = 0;
     uint8_t *d_tail = nullptr;               // private output of the last-frame launch
     unsigned long long *d_tail_meta = nullptr;  // [0] desc, [1] total, [2] lo32: frame size
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
@@ -87,7 +90,9 @@ struct zf_encoder {
     size_t max_frame_bytes = 0;
     bool stereo = false;
     bool force_legacy = false;  // ZF_LEGACY_KERNEL=1: A/B against the 512-thread kernel (development aid)
-    int occ_full = 0, occ_gen = 0, occ_v3 = 0;
+    int occ_full = 0, occ_gen = 0, occ_v3 = 0, occ_lpc = 0;
+    size_t smem_lpc = 0;
+    uint16_t *d_win = nullptr;  // LPC: window of a full block
     size_t smem_stereo = 0;
     size_t smem_v3 = 0;
     size_t smem_indep = 0;
@@ -158,6 +163,27 @@ int setup_v3_kernel(zf_encoder *e, int *occ) {
 }
 
 template <int BYTES>
+int setup_lpc_kernel(zf_encoder *e, int *occ) {
+    auto k = zf::lpc::zf_encode_stereo_lpc_kernel<BYTES>;
+    const size_t smem = sizeof(zf::lpc::SmemLpc<BYTES>);
+    ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, zf::kThreads, smem));
+    e->smem_lpc = smem;
+    return ZF_OK;
+}
+
+// zf-LPC v1 window (zf_kernel_lpc.cuh): W[i] = 16384 - floor((2i - (n-1))^2 * 16384 / (n-1)^2)
+void lpc_window(uint32_t n, std::vector<uint16_t> &w) {
+    w.assign(n, 16384);
+    if (n <= 1) return;
+    const unsigned long long den = (unsigned long long)(n - 1) * (n - 1);
+    for (uint32_t i = 0; i < n; i++) {
+        const long long d = 2ll * i - (long long)(n - 1);
+        w[i] = (uint16_t)(16384u - (uint32_t)((((unsigned long long)(d * d)) << 14) / den));
+    }
+}
+
+template <int BYTES>
 int setup_indep_kernel(zf_encoder *e, int *occ) {
     auto k = zf::zf_encode_indep_kernel<BYTES>;
     const size_t smem = zf::indep_smem_bytes(BYTES, e->cfg.channels);
@@ -179,6 +205,14 @@ int setup_kernels(zf_encoder *e) {
         else if (bytes == 3) rc = setup_indep_kernel<3>(e, &e->occ_gen);
         else rc = setup_indep_kernel<4>(e, &e->occ_gen);
         e->occ_full = e->occ_gen;
+    }
+    if (!rc && e->cfg.lpc_order) {
+        if (bytes == 2) rc = setup_lpc_kernel<2>(e, &e->occ_lpc);
+        else rc = setup_lpc_kernel<3>(e, &e->occ_lpc);
+        if (!rc && e->occ_lpc < 1) {
+            snprintf(g_cuda_err, sizeof g_cuda_err, "LPC kernel does not fit on an SM");
+            rc = ZF_ERR_CUDA;
+        }
     }
     if (rc) return rc;
     if (e->occ_full < 1 || e->occ_gen < 1) {
@@ -213,6 +247,11 @@ void launch_stereo(bool full, int grid, size_t smem, cudaStream_t s, bool overla
 
 void launch_one(zf_encoder *e, bool full, int grid, cudaStream_t s, const zf::FrameJob &job, bool overlap = false) {
     const int bytes = container_bytes(e->cfg);
+    if (e->cfg.lpc_order) {
+        if (bytes == 2) launch_k(zf::lpc::zf_encode_stereo_lpc_kernel<2>, grid, zf::kThreads, e->smem_lpc, s, overlap, job);
+        else launch_k(zf::lpc::zf_encode_stereo_lpc_kernel<3>, grid, zf::kThreads, e->smem_lpc, s, overlap, job);
+        return;
+    }
     if (e->stereo) {
         if (bytes == 2) launch_stereo<2>(full, grid, e->smem_stereo, s, overlap, job);
         else if (bytes == 3) launch_stereo<3>(full, grid, e->smem_stereo, s, overlap, job);
@@ -253,6 +292,8 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     job.first_frame_number = first_frame_number;
     job.frame_stride = (uint32_t)e->frame_dev_bytes;
     job.bit_depth = e->cfg.bit_depth;
+    job.lpc_order = e->cfg.lpc_order;
+    job.lpc_window = e->d_win;
     job.sample_rate = e->cfg.sample_rate;
     job.channels = e->cfg.channels;
     job.max_rice_order = e->cfg.max_rice_order;
@@ -266,7 +307,15 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         (*launches)++;
     }
     // the fast kernel covers the reference's default shape: 4096-sample frames, max_rice_order 8, 16/24/32-bit samples
-    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.max_rice_order == 8 && e->cfg.bit_depth != 8;
+    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.max_rice_order == 8 && e->cfg.bit_depth != 8 &&
+                      !e->cfg.lpc_order;
+    if (e->cfg.lpc_order && tail && sl.win_tail_len != tail) {  // the short last frame has a window of its own length
+        std::vector<uint16_t> w;
+        lpc_window(tail, w);
+        if (!sl.d_win_tail) ZF_CUDA(cudaMalloc(&sl.d_win_tail, sizeof(uint16_t) * zf::kMaxBlock));
+        ZF_CUDA(cudaMemcpyAsync(sl.d_win_tail, w.data(), sizeof(uint16_t) * tail, cudaMemcpyHostToDevice, s));  // pageable: staged at once
+        sl.win_tail_len = tail;
+    }
     // the 1-D TMA bulk copy needs 16-byte aligned sources; frame strides are multiples of 16 already
     job.use_tma = ((uintptr_t)d_pcm & 15u) == 0 ? 1u : 0u;
     // The short last frame is a one-CTA launch of the general kernel IN FRONT of the persistent full-frame kernel, which is
@@ -288,6 +337,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         tj.batch_frames = 1;
         tj.first_frame_number = first_frame_number + full;
         tj.block_size = tail;
+        tj.lpc_window = sl.d_win_tail;
         tj.ticket = sl.d_ctl + 1;
         tj.pdl_trigger = 1;
         launch_one(e, false, 1, s, tj);
@@ -303,7 +353,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         // 16/24-bit with the default Rice limits: the lean 256-thread kernel (zf_kernel_v3.cuh)
         const bool v3 = fast && e->cfg.max_rice_param == 30 && e->occ_v3 > 0 && !e->force_legacy &&
                         table_rate(e->cfg.sample_rate);
-        const int occ = v3 ? e->occ_v3 : fast ? e->occ_full : e->occ_gen;
+        const int occ = e->cfg.lpc_order ? e->occ_lpc : v3 ? e->occ_v3 : fast ? e->occ_full : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
         if (v3) {
             if (e->cfg.bit_depth == 16) launch_k(zf::v3::zf_encode_stereo_v3_kernel<2>, grid, zf::v3::kT, e->smem_v3, s, split_tail, job);
@@ -325,6 +375,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         job.n_frames = 1;
         job.frame_base = 0;
         job.block_size = tail;
+        job.lpc_window = sl.d_win_tail;
         job.ticket = sl.d_ctl + 1;
         launch_one(e, false, 1, s, job);
         (*launches)++;
@@ -370,6 +421,7 @@ int slot_init(zf_encoder *e, Slot &sl) {
 void slot_free(Slot &sl) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
     cudaFree(sl.d_tail);
+    cudaFree(sl.d_win_tail);
     cudaFree(sl.d_wide);
     cudaFree(sl.d_pcm); cudaFree(sl.d_out); cudaFree(sl.d_sizes); cudaFree(sl.d_ctl_block); cudaFree(sl.d_total);
     cudaFreeHost(sl.h_pcm); cudaFreeHost(sl.h_out); cudaFreeHost(sl.h_sizes); cudaFreeHost(sl.h_total);
@@ -557,6 +609,10 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     if (cfg->max_rice_order > 8) return ZF_ERR_UNSUPPORTED;            // rice.MAX_ORDER = 8 (rice.zig:12)
     if (cfg->max_rice_param == 0 || cfg->max_rice_param > 30) return ZF_ERR_UNSUPPORTED;  // 0: overflow upstream
     if (cfg->max_frames_per_batch == 0) return ZF_ERR_INVALID_ARG;
+    if (cfg->lpc_order) {  // the LPC extension (no reference counterpart): stereo with decorrelation, 8/16/24-bit, order <= 12
+        if (cfg->lpc_order > zf::lpc::kMaxOrder || cfg->channels != 2 || !cfg->stereo_decorrelation || cfg->bit_depth == 32)
+            return ZF_ERR_UNSUPPORTED;
+    }
     int rc = zf_device_check(cfg->device_id);
     if (rc) return rc;
     ZF_CUDA(cudaSetDevice(cfg->device_id));
@@ -593,6 +649,13 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
             rc = ZF_ERR_CUDA;
         }
     }
+    if (!rc && cfg->lpc_order) {
+        std::vector<uint16_t> w;
+        lpc_window(cfg->block_size, w);
+        cudaError_t ce = cudaMalloc(&e->d_win, sizeof(uint16_t) * zf::kMaxBlock);
+        if (ce == cudaSuccess) ce = cudaMemcpy(e->d_win, w.data(), sizeof(uint16_t) * w.size(), cudaMemcpyHostToDevice);
+        if (ce != cudaSuccess) rc = ZF_ERR_CUDA;
+    }
     if (rc) {
         zf_encoder_destroy(e);
         return rc;
@@ -611,6 +674,7 @@ void zf_encoder_destroy(zf_encoder *e) {
     if (e->s_down) cudaStreamDestroy(e->s_down);
     if (e->ev_dev) cudaEventDestroy(e->ev_dev);
     cudaFree(e->d_pow8);
+    cudaFree(e->d_win);
     for (cudaEvent_t ev : e->tr_ev) cudaEventDestroy(ev);
     delete e;
 }

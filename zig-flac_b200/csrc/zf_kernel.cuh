@@ -68,6 +68,8 @@ struct FrameJob {
     uint32_t max_rice_order;
     uint32_t max_rice_param;
     uint32_t use_tma;
+    const uint16_t *lpc_window;    // LPC kernel: integer Welch window of this launch's block size (zf_kernel_lpc.cuh)
+    uint32_t lpc_order;            // LPC kernel: maximum order
     uint32_t bit_depth;            // general kernels: sample depth when it is not the container's (8-bit samples travel in
                                    // 16-bit containers); 0 = 8 x container bytes
     uint32_t pdl_trigger;          // general kernels: release the dependent launch at once (the one-CTA last-frame
