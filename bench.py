@@ -411,7 +411,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
                          "traffic_source": (ncu or {}).get("file"), "issue": issue,
-                         "kernel": ("zf::lpc::zf_encode_stereo_lpc_kernel<%d>" % (bits // 8)) if args.workload in LPC_ORDER else ("zf::v3::zf_encode_stereo_v3_kernel<%d>" % (bits // 8)) if not os.environ.get("ZF_LEGACY_KERNEL") else ("zf::zf_encode_stereo_full_kernel<%d>" % (bits // 8)),
+                         "kernel": ("zf::lpc::zf_encode_stereo_lpc_kernel<%d>" % (bits // 8)) if args.workload in LPC_ORDER else ("zf::v3::zf_encode_stereo_v3_kernel<%d>" % (bits // 8)),
                          "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": kernel_bytes,
                          "peak_source": peak_src,
                          "note": "bound is nominal: the kernel is integer-issue bound (see `issue`), HBM is mostly idle; DESIGN.md section 4"},

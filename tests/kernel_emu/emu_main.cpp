@@ -13,7 +13,6 @@ namespace zf { alignas(128) unsigned char zf_smem[256 * 1024]; namespace v3 { al
 
 #include "../../zig-flac_b200/csrc/zf_kernel.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_indep.cuh"
-#include "../../zig-flac_b200/csrc/zf_kernel_full.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_v3.cuh"
 #include "../../zig-flac_b200/csrc/zf_kernel_lpc.cuh"
 
@@ -144,12 +143,6 @@ static void kernel_entry(void *) {
         else zf::v3::zf_encode_stereo_v3_kernel<4>(g_job);
         return;
     }
-    if (g_full) {
-        if (g_bytes == 2) zf::zf_encode_stereo_full_kernel<2>(g_job);
-        else if (g_bytes == 3) zf::zf_encode_stereo_full_kernel<3>(g_job);
-        else zf::zf_encode_stereo_full_kernel<4>(g_job);
-        return;
-    }
     if (g_bytes == 2) zf::zf_encode_stereo_kernel<2, false>(g_job);
     else if (g_bytes == 3) zf::zf_encode_stereo_kernel<3, false>(g_job);
     else zf::zf_encode_stereo_kernel<4, false>(g_job);
@@ -198,9 +191,7 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
         j.pcm = pcm; j.n_frames = (uint32_t)full; j.frame_base = 0; j.block_size = block_size;
         g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8 && g_bit_depth == 0 && !g_lpc_order;
         if (g_lpc_order) { make_window(block_size); j.lpc_window = g_win.data(); }
-        bool table = false;
-        for (unsigned r : {88200u, 176400u, 192000u, 8000u, 16000u, 22050u, 24000u, 32000u, 44100u, 48000u, 96000u}) table |= r == sample_rate;
-        g_v3 = g_full && g_allow_v3 && max_rice_param == 30 && table && g_bit_depth == 0;
+        g_v3 = g_full && g_allow_v3 && g_bit_depth == 0;
         g_job = j;
         ticket = 0;
         if (g_v3) g_v3_frames += full;

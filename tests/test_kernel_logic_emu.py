@@ -23,7 +23,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "zig-flac_b200", "csrc")
 @pytest.fixture(scope="module")
 def emu():
     srcs = [os.path.join(EMU_DIR, f) for f in ("emu_main.cpp", "cuda_emu.h")] + [
-        os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_kernel_full.cuh", "zf_kernel_v3.cuh", "zf_kernel_lpc.cuh", "zf_dev.h")]
+        os.path.join(CSRC, f) for f in ("zf_kernel.cuh", "zf_kernel_indep.cuh", "zf_kernel_v3.cuh", "zf_kernel_lpc.cuh", "zf_dev.h")]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(s) > os.path.getmtime(EMU_SO) for s in srcs):
         os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
         subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", EMU_SO,
@@ -276,3 +276,20 @@ def test_lpc_kernel_logic(emu, oracle, bits):
     finally:
         emu.emu_set_lpc_order(0)
     assert n_lpc > 10  # LPC subframes really were chosen and written
+
+
+@pytest.mark.parametrize("bits", [16, 24, 32])
+def test_v3_kernel_any_rice_limit_and_sample_rate(emu, oracle, bits):
+    """The lean kernel covers every max_rice_param (1 = parameter 0 only, rice.zig:369) and sample rates without a header
+    code of their own, whose trailer carries the block size upstream (frame_writer.zig:258-262)."""
+    import zigflac_b200 as zf
+    emu.emu_v3_frames.restype = C.c_ulonglong
+    n = 2 * 4096
+    pcm = zf.synth_pcm(n, 96000, bits, first_sample=300000)
+    before = emu.emu_v3_frames()
+    for mrp in (1, 2, 5, 14, 15, 29, 30):
+        _check(emu, oracle, pcm, n, bits, rate=96000, mrp=mrp)
+    for rate in (200, 255, 256, 11025, 12345, 65535, 65536, 100000, 1048575):
+        _check(emu, oracle, pcm, n, bits, rate=rate, first=(1 << 21) + 3)
+        _check(emu, oracle, pcm, n, bits, rate=rate, first=5)
+    assert emu.emu_v3_frames() - before == 2 * (7 + 18)

@@ -17,7 +17,6 @@
 #include "../../include/zigflac_b200.h"
 #include "zf_kernel.cuh"
 #include "zf_kernel_indep.cuh"
-#include "zf_kernel_full.cuh"
 #include "zf_kernel_v3.cuh"
 #include "zf_kernel_lpc.cuh"
 
@@ -89,8 +88,7 @@ struct zf_encoder {
     size_t frame_dev_bytes = 0;   // ... and as the kernels read it (differs for 8-bit samples)
     size_t max_frame_bytes = 0;
     bool stereo = false;
-    bool force_legacy = false;  // ZF_LEGACY_KERNEL=1: A/B against the 512-thread kernel (development aid)
-    int occ_full = 0, occ_gen = 0, occ_v3 = 0, occ_lpc = 0;
+    int occ_gen = 0, occ_v3 = 0, occ_lpc = 0;
     size_t smem_lpc = 0;
     uint16_t *d_win = nullptr;  // LPC: window of a full block
     size_t smem_stereo = 0;
@@ -123,15 +121,6 @@ bool depth_ok(unsigned d) { return d == 8 || d == 16 || d == 24 || d == 32; }
 // bytes per sample inside the kernels: 8-bit samples are widened to 16-bit containers on the device first
 int container_bytes(const zf_config &cfg) { return cfg.bit_depth == 8 ? 2 : cfg.bit_depth / 8; }
 
-// sample rates with a frame-header code of their own (frame_writer.zig:187-217); others take the general kernels
-bool table_rate(uint32_t r) {
-    switch (r) {
-        case 88200: case 176400: case 192000: case 8000: case 16000: case 22050: case 24000: case 32000: case 44100:
-        case 48000: case 96000: return true;
-        default: return false;
-    }
-}
-
 size_t max_frame_bytes_of(const zf_config *cfg) {
     // encoder.zig:583-595 with the reference's own call-site quirk (:59 passes compute_waste_bits = true)
     const size_t header_max = 2 + 7 + 2 + 2 + 1, subframe_header_max = 8, footer = 2;
@@ -141,10 +130,9 @@ size_t max_frame_bytes_of(const zf_config *cfg) {
            footer;
 }
 
-template <int BYTES, bool FULL>
+template <int BYTES>
 int setup_stereo_kernel(zf_encoder *e, int *occ) {
     void (*k)(const zf::FrameJob) = zf::zf_encode_stereo_kernel<BYTES, false>;
-    if (FULL) k = zf::zf_encode_stereo_full_kernel<BYTES>;
     const size_t smem = sizeof(zf::SmemStereo<BYTES>);
     ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ZF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, zf::kThreads, smem));
@@ -197,14 +185,13 @@ int setup_kernels(zf_encoder *e) {
     const int bytes = container_bytes(e->cfg);
     int rc = ZF_OK;
     if (e->stereo) {
-        if (bytes == 2) { rc = setup_stereo_kernel<2, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<2, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<2>(e, &e->occ_v3); }
-        else if (bytes == 3) { rc = setup_stereo_kernel<3, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<3, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<3>(e, &e->occ_v3); }
-        else { rc = setup_stereo_kernel<4, true>(e, &e->occ_full); if (!rc) rc = setup_stereo_kernel<4, false>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<4>(e, &e->occ_v3); }
+        if (bytes == 2) { rc = setup_stereo_kernel<2>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<2>(e, &e->occ_v3); }
+        else if (bytes == 3) { rc = setup_stereo_kernel<3>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<3>(e, &e->occ_v3); }
+        else { rc = setup_stereo_kernel<4>(e, &e->occ_gen); if (!rc) rc = setup_v3_kernel<4>(e, &e->occ_v3); }
     } else {
         if (bytes == 2) rc = setup_indep_kernel<2>(e, &e->occ_gen);
         else if (bytes == 3) rc = setup_indep_kernel<3>(e, &e->occ_gen);
         else rc = setup_indep_kernel<4>(e, &e->occ_gen);
-        e->occ_full = e->occ_gen;
     }
     if (!rc && e->cfg.lpc_order) {
         if (bytes == 2) rc = setup_lpc_kernel<2>(e, &e->occ_lpc);
@@ -215,7 +202,7 @@ int setup_kernels(zf_encoder *e) {
         }
     }
     if (rc) return rc;
-    if (e->occ_full < 1 || e->occ_gen < 1) {
+    if (e->occ_gen < 1) {
         snprintf(g_cuda_err, sizeof g_cuda_err, "kernel does not fit on an SM (occupancy 0)");
         return ZF_ERR_CUDA;
     }
@@ -240,12 +227,12 @@ void launch_k(K kernel, int grid, int block, size_t smem, cudaStream_t s, bool o
 }
 
 template <int BYTES>
-void launch_stereo(bool full, int grid, size_t smem, cudaStream_t s, bool overlap, const zf::FrameJob &job) {
-    if (full) launch_k(zf::zf_encode_stereo_full_kernel<BYTES>, grid, zf::kThreads, smem, s, overlap, job);
-    else launch_k(zf::zf_encode_stereo_kernel<BYTES, false>, grid, zf::kThreads, smem, s, overlap, job);
+void launch_stereo(int grid, size_t smem, cudaStream_t s, bool overlap, const zf::FrameJob &job) {
+    launch_k(zf::zf_encode_stereo_kernel<BYTES, false>, grid, zf::kThreads, smem, s, overlap, job);
 }
 
-void launch_one(zf_encoder *e, bool full, int grid, cudaStream_t s, const zf::FrameJob &job, bool overlap = false) {
+// the general kernels: LPC, stereo of any geometry, independent channels
+void launch_one(zf_encoder *e, int grid, cudaStream_t s, const zf::FrameJob &job, bool overlap = false) {
     const int bytes = container_bytes(e->cfg);
     if (e->cfg.lpc_order) {
         if (bytes == 2) launch_k(zf::lpc::zf_encode_stereo_lpc_kernel<2>, grid, zf::kThreads, e->smem_lpc, s, overlap, job);
@@ -253,9 +240,9 @@ void launch_one(zf_encoder *e, bool full, int grid, cudaStream_t s, const zf::Fr
         return;
     }
     if (e->stereo) {
-        if (bytes == 2) launch_stereo<2>(full, grid, e->smem_stereo, s, overlap, job);
-        else if (bytes == 3) launch_stereo<3>(full, grid, e->smem_stereo, s, overlap, job);
-        else launch_stereo<4>(full, grid, e->smem_stereo, s, overlap, job);
+        if (bytes == 2) launch_stereo<2>(grid, e->smem_stereo, s, overlap, job);
+        else if (bytes == 3) launch_stereo<3>(grid, e->smem_stereo, s, overlap, job);
+        else launch_stereo<4>(grid, e->smem_stereo, s, overlap, job);
     } else {
         if (bytes == 2) launch_k(zf::zf_encode_indep_kernel<2>, grid, zf::kThreads, e->smem_indep, s, overlap, job);
         else if (bytes == 3) launch_k(zf::zf_encode_indep_kernel<3>, grid, zf::kThreads, e->smem_indep, s, overlap, job);
@@ -340,7 +327,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         tj.lpc_window = sl.d_win_tail;
         tj.ticket = sl.d_ctl + 1;
         tj.pdl_trigger = 1;
-        launch_one(e, false, 1, s, tj);
+        launch_one(e, 1, s, tj);
         (*launches)++;
     }
     if (full) {
@@ -350,17 +337,16 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         job.block_size = bs;
         job.ticket = sl.d_ctl + 0;
         if (split_tail) job.batch_frames = (uint32_t)full;  // the full-frame kernel closes its own total
-        // 16/24-bit with the default Rice limits: the lean 256-thread kernel (zf_kernel_v3.cuh)
-        const bool v3 = fast && e->cfg.max_rice_param == 30 && e->occ_v3 > 0 && !e->force_legacy &&
-                        table_rate(e->cfg.sample_rate);
-        const int occ = e->cfg.lpc_order ? e->occ_lpc : v3 ? e->occ_v3 : fast ? e->occ_full : e->occ_gen;
+        // full 4096-sample stereo frames with the reference's partition depth: the lean 256-thread kernel (zf_kernel_v3.cuh)
+        const bool v3 = fast && e->occ_v3 > 0;
+        const int occ = e->cfg.lpc_order ? e->occ_lpc : v3 ? e->occ_v3 : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
         if (v3) {
             if (e->cfg.bit_depth == 16) launch_k(zf::v3::zf_encode_stereo_v3_kernel<2>, grid, zf::v3::kT, e->smem_v3, s, split_tail, job);
             else if (e->cfg.bit_depth == 24) launch_k(zf::v3::zf_encode_stereo_v3_kernel<3>, grid, zf::v3::kT, e->smem_v3, s, split_tail, job);
             else launch_k(zf::v3::zf_encode_stereo_v3_kernel<4>, grid, zf::v3::kT, e->smem_v3, s, split_tail, job);
         } else {
-            launch_one(e, fast, grid, s, job, split_tail);
+            launch_one(e, grid, s, job, split_tail);
         }
         ZF_CUDA(cudaEventRecord(sl.kev[2 * ring + 1], s));
         sl.kev_count++;
@@ -377,7 +363,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         job.block_size = tail;
         job.lpc_window = sl.d_win_tail;
         job.ticket = sl.d_ctl + 1;
-        launch_one(e, false, 1, s, job);
+        launch_one(e, 1, s, job);
         (*launches)++;
     }
     ZF_CUDA(cudaGetLastError());
@@ -620,7 +606,6 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     if (!e) return ZF_ERR_NOMEM;
     e->cfg = *cfg;
     e->stereo = cfg->channels == 2 && cfg->stereo_decorrelation;
-    { const char *lg = getenv("ZF_LEGACY_KERNEL"); e->force_legacy = lg && lg[0] == '1'; }
     { const char *tr = getenv("ZF_TRACE"); e->trace = tr && tr[0] == '1'; }
     { const char *nt = getenv("ZF_NO_TAPER"); e->no_taper = nt && nt[0] == '1'; }  // A/B of the batch plan (development aid)
     e->frame_pcm_bytes = (size_t)cfg->block_size * cfg->channels * (cfg->bit_depth / 8);

@@ -414,9 +414,10 @@ ZF_DEVICE void best_param_nw(unsigned long long S, uint32_t B, uint32_t n, uint3
     }
     uint32_t p = q + 1u;
     if (p > P - 1u) p = P - 1u;
-    const unsigned long long sh = S >> (p - 1u);
+    const unsigned long long sh = S >> ((p - 1u) & 63u);
     const uint32_t sh32 = sh > 0x3fffffffull ? 0x3fffffffu : (uint32_t)sh;
     uint32_t cc = (1u + p) * n + sh32 - (n >> 1);
+    if (p == 0u) cc = 0xffffffffu;  // max_rice_param 1: only parameter 0 is tried (rice.zig:369)
     uint32_t cand = p;
     const uint32_t c0 = S > 0x0fffffffull ? 0x7fffffffu : n + 2u * (uint32_t)S;  // p == 0: no -(n >> 1)
     if (c0 <= cc) { cc = c0; cand = 0; }                                         // lowest p wins ties
@@ -436,9 +437,10 @@ ZF_DEVICE void best_param_w(unsigned long long S, uint32_t B, uint32_t n, uint32
     }
     uint32_t p = q + 1u;
     if (p > P - 1u) p = P - 1u;
-    const unsigned long long sh = S >> (p - 1u);
+    const unsigned long long sh = S >> ((p - 1u) & 63u);
     const uint32_t sh32 = sh > 0x3fffffffull ? 0x3fffffffu : (uint32_t)sh;
     uint32_t cc = (1u + p) * n + sh32 - (n >> 1);
+    if (p == 0u) cc = 0xffffffffu;  // max_rice_param 1: only parameter 0 is tried (rice.zig:369)
     uint32_t cand = p;
     const uint32_t c0 = S > 0x0fffffffull ? 0x7fffffffu : n + 2u * (uint32_t)S;
     if (c0 <= cc) { cc = c0; cand = 0; }
@@ -458,9 +460,10 @@ ZF_DEVICE void best_param_32(uint32_t S, uint32_t B, uint32_t n, uint32_t P, uin
     }
     uint32_t p = q + 1u;
     if (p > P - 1u) p = P - 1u;
-    const uint32_t sh = S >> (p - 1u);
+    const uint32_t sh = S >> ((p - 1u) & 31u);
     const uint32_t sh32 = sh > 0x3fffffffu ? 0x3fffffffu : sh;
     uint32_t cc = (1u + p) * n + sh32 - (n >> 1);
+    if (p == 0u) cc = 0xffffffffu;  // max_rice_param 1: only parameter 0 is tried (rice.zig:369)
     uint32_t cand = p;
     const uint32_t c0 = S > 0x0fffffffu ? 0x7fffffffu : n + 2u * S;
     if (c0 <= cc) { cc = c0; cand = 0; }
@@ -882,14 +885,16 @@ ZF_NOINLINE void copy_out(const Smem<BYTES> &sm, uint8_t *out, unsigned long lon
 }
 
 // Frame header (frame_writer.zig:151-265) + CRC-8 (:128-141), one byte per lane of one warp.  Covers what this kernel
-// is launched for: block size 4096 (code 12, no trailer), a sample rate from the table (codes 1..11, no trailer),
-// frame numbers below 2^31.  Returns this lane's byte; `len` is the header length including the CRC-8.
+// is launched for: block size 4096 (code 12, no block-size trailer), frame numbers below 2^31, any sample rate: one
+// from the table has a code of its own (1..11), any other takes code 12 / 13 / 14 and a trailer of `rate_extra`
+// bytes -- into which the reference writes the BLOCK SIZE (frame_writer.zig:258-262), reproduced here.
+// Returns this lane's byte; `len` is the header length including the CRC-8.
 ZF_DEVICE uint32_t header_byte(const uint8_t *crc8tab, int lane, unsigned long long frame_number, uint32_t depth,
-                               uint32_t ch_type, uint32_t rate_code_v, uint32_t &len) {
+                               uint32_t ch_type, uint32_t rate_code_v, uint32_t rate_extra, uint32_t &len) {
     const uint32_t fn = (uint32_t)frame_number;
     // UTF-8-like number coder (:235-251): i continuation bytes of 6 bits, lowest group last
     const uint32_t i = fn < 0x80u ? 0u : fn < 0x800u ? 1u : fn < 0x10000u ? 2u : fn < 0x200000u ? 3u : fn < 0x4000000u ? 4u : 5u;
-    len = 4u + 1u + i + 1u;
+    len = 4u + 1u + i + rate_extra + 1u;
     const uint32_t dc = depth == 16 ? 8u : depth == 24 ? 12u : 14u;  // :221-233
     uint32_t b = 0;
     const uint32_t k = (uint32_t)lane;
@@ -902,7 +907,13 @@ ZF_DEVICE uint32_t header_byte(const uint8_t *crc8tab, int lane, unsigned long l
         const uint32_t gi = 4u + i - k;  // group index, 0 = least significant
         b = 0x80u + ((fn >> (6u * gi)) & 0x3fu);
         if (gi == 4u) b &= 0x0Fu;  // u36 shift truncation in the reference for numbers >= 2^26
+    } else if (k <= 4u + i + rate_extra) {
+        // :260-261: the block size where the rate should be -- 8 bits (code 12), 16 bits (13), block size / 10 (14)
+        const uint32_t v = rate_code_v == 14u ? (uint32_t)kN / 10u : (uint32_t)kN;
+        b = (rate_extra == 2u && k == 5u + i) ? (v >> 8) : (v & 0xFFu);
     }
+    // :260 writes the 13-bit block size through an 8-bit field: its high bits OR into the byte in front (Q10)
+    if (rate_extra == 1u && k == 4u + i) b |= (uint32_t)kN >> 8;
     // CRC-8 (poly 0x07, init 0) is linear: byte k contributes T^(len-1-k)[byte], T = one table step
     uint32_t v = (k < len - 1u) ? b : 0u;
     const uint32_t steps = len - 1u - (k < len - 1u ? k : len - 1u);
@@ -1040,7 +1051,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         fetch_frame<BYTES>(sm, job.pcm + (size_t)f * job.frame_stride, warp);
     }
     uint32_t rate_extra;
-    const uint32_t rate_code_v = rate_code(job.sample_rate, rate_extra);  // a table rate: no trailer (checked on the host)
+    const uint32_t rate_code_v = rate_code(job.sample_rate, rate_extra);
     LbArgs lba;
     lba.desc = job.desc; lba.total_bytes = job.total_bytes; lba.status = job.status; lba.out_cap = job.out_cap;
     lba.batch_frames = job.batch_frames;
@@ -1513,10 +1524,10 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         }
         uint32_t ex_a, ex_b, tot_a, tot_b;
         block_scan2(sm.scan, t, len_a, len_b, ex_a, ex_b, tot_a, tot_b);
-        // 4 fixed bytes + the UTF-8-like frame number + CRC-8 (block size 4096 and table sample rates have no trailer)
+        // 4 fixed bytes + the UTF-8-like frame number + the trailer of a sample rate without a code + CRC-8
         const uint32_t fn32 = (uint32_t)frame_number;
-        const uint32_t hdr_bits = 8u * (6u + (fn32 >= 0x80u) + (fn32 >= 0x800u) + (fn32 >= 0x10000u) + (fn32 >= 0x200000u) +
-                                        (fn32 >= 0x4000000u));
+        const uint32_t hdr_bits = 8u * (6u + rate_extra + (fn32 >= 0x80u) + (fn32 >= 0x800u) + (fn32 >= 0x10000u) +
+                                        (fn32 >= 0x200000u) + (fn32 >= 0x4000000u));
         const uint32_t total_bits = hdr_bits + tot_a + tot_b;
         const uint32_t fbytes = (total_bits + 7u) >> 3;
         const uint32_t size = fbytes + 2u;
@@ -1604,7 +1615,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         // frame header, one byte per lane of the last warp: worked out in front of the barrier (between the two barriers
         // the other seven warps would only wait for it), ORed in behind it
         uint32_t hbyte = 0, hlen = 0;
-        if (fits && warp == kW - 1) hbyte = header_byte(sm.crc8tab, lane, frame_number, depth, ch_type, rate_code_v, hlen);
+        if (fits && warp == kW - 1) hbyte = header_byte(sm.crc8tab, lane, frame_number, depth, ch_type, rate_code_v, rate_extra, hlen);
         __syncthreads();  // all complete words stored
         if (fits) {
             wa.or_tail();
