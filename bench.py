@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-file", action="store_true", help="skip the whole-file (WAV -> FLAC, MD5 included) leg")
     ap.add_argument("--profile", action="store_true", help="device-resident steps only (for runs under ncu)")
     return ap.parse_args()
 
@@ -364,6 +365,36 @@ def main():
         dist.all_reduce(tc, op=dist.ReduceOp.MAX)
     copy_s = float(tc.item())
 
+    # ---- whole file: WAV bytes -> FLAC bytes through zf_encode_wav_memory (what `flac in.wav out.flac` does after the read:
+    #      parse, MD5 of the PCM on a host thread, chunked encode, STREAMINFO back-patch); the serial MD5 bounds it ----
+    e2e_file = None
+    if world == 1 and not args.no_e2e_file and pcm_bytes < (1 << 32) - 64:
+        import struct
+        fmt_chunk = struct.pack("<HHIIHH", 1, CHANNELS, rate, rate * ic_bytes, ic_bytes, bits)
+        head = b"RIFF" + struct.pack("<I", 4 + 8 + len(fmt_chunk) + 8 + pcm_bytes) + b"WAVE" + b"fmt " + \
+            struct.pack("<I", len(fmt_chunk)) + fmt_chunk + b"data" + struct.pack("<I", pcm_bytes)
+        wav = np.empty(len(head) + pcm_bytes, dtype=np.uint8)
+        wav[:len(head)] = np.frombuffer(head, dtype=np.uint8)
+        wav[len(head):] = h_pcm_np
+        if LPC_ORDER.get(args.workload, 0) == 0:  # the driver mirrors the reference CLI: Config.default, no LPC
+            rc, flac = zf.wav_to_flac(wav, devices=[local_rank])  # warm-up (page-locks its chunk buffers)
+            file_steps = 2
+            t0 = time.perf_counter()
+            for _ in range(file_steps):
+                rc, flac = zf.wav_to_flac(wav, devices=[local_rank])
+            file_s = (time.perf_counter() - t0) / file_steps
+            md5 = zf.Md5()
+            t0 = time.perf_counter()
+            md5.update(h_pcm_np)
+            digest = md5.final()
+            md5_s = time.perf_counter() - t0
+            e2e_file = {"value": round(nsamples * CHANNELS / file_s / 1e6, 2), "unit": UNIT, "ms_per_file": round(file_s * 1e3, 2),
+                        "md5_only_ms": round(md5_s * 1e3, 2), "flac_bytes": len(flac) if flac else None, "status": rc,
+                        "md5_matches_streaminfo": bool(flac and flac[26:42] == digest),
+                        "api": "zf_encode_wav_memory (reader | MD5 thread | encoder | writer pipeline over 2048-frame chunks)",
+                        "note": "bounded by the serial MD5 of the PCM (md5_only_ms), which the reference computes too"}
+        del wav
+
     # the device-resident result and the host-path result are the same bytes
     same = bool((d_out[:flac_bytes].cpu().numpy() == got).all()) and flac_bytes == int(got.size)
 
@@ -407,6 +438,7 @@ def main():
                     "d2h_bytes_per_step": all_e2e_out, "ms_per_step": round(e2e_s * 1e3, 3), "steps": e2e_steps,
                     "copy_ceiling_ms": round(copy_s * 1e3, 3), "frac_of_copy_ceiling": round(copy_s / e2e_s, 4),
                     "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 2048-frame batches, pipeline: upload | encode | download on three streams)"},
+            "e2e_file": e2e_file,
             "gpu_launches": all_launches,  # all ranks, timed region of the device-resident arm
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),
