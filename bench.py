@@ -392,7 +392,25 @@ def main():
                         "md5_only_ms": round(md5_s * 1e3, 2), "flac_bytes": len(flac) if flac else None, "status": rc,
                         "md5_matches_streaminfo": bool(flac and flac[26:42] == digest),
                         "api": "zf_encode_wav_memory (reader | MD5 thread | encoder | writer pipeline over 2048-frame chunks)",
-                        "note": "bounded by the serial MD5 of the PCM (md5_only_ms), which the reference computes too"}
+                        "note": "warm library call; bounded by the serial MD5 of the PCM (md5_only_ms), which the reference computes too"}
+            # ... and the CLI as a user runs it: a fresh process (CUDA context creation included), files on tmpfs
+            cli = os.path.join(ROOT, "zig-flac_b200", "flac")
+            shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+            if os.path.exists(cli):
+                import subprocess
+                fin, fout = os.path.join(shm, f"zf_bench_{os.getpid()}.wav"), os.path.join(shm, f"zf_bench_{os.getpid()}.flac")
+                try:
+                    wav.tofile(fin)
+                    t0 = time.perf_counter()
+                    r = subprocess.run([cli, fin, fout], capture_output=True)
+                    cli_s = time.perf_counter() - t0
+                    same_file = r.returncode == 0 and flac is not None and open(fout, "rb").read() == flac
+                    e2e_file["cli"] = {"wall_ms": round(cli_s * 1e3, 1), "exit": r.returncode, "same_bytes_as_library": bool(same_file),
+                                       "note": "`flac in.wav out.flac` in a fresh process: process start, CUDA context, file I/O on tmpfs included"}
+                finally:
+                    for f in (fin, fout):
+                        if os.path.exists(f):
+                            os.remove(f)
         del wav
 
     # the device-resident result and the host-path result are the same bytes

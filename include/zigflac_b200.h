@@ -217,6 +217,9 @@ int zf_encode_wav_file(const char *in_path, const char *out_path, const int *dev
 int zf_encode_wav_memory(const uint8_t *wav, size_t wav_len, uint8_t **flac, size_t *flac_len, const int *devices,
                          int n_devices);
 void zf_free(void *p);
+/* The whole-file driver keeps its encoder handles and page-locked chunk buffers between calls (creating them costs more than
+ * encoding a short file); whole-file calls of one process are serialised.  This releases them. */
+void zf_driver_release_cache(void);
 
 /*
  * Page-locked host memory for PCM / FLAC buffers (the counterpart of the sample buffer wav2flac.zig:72 takes from its

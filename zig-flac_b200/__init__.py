@@ -128,6 +128,7 @@ def _lib():
     L.zf_encode_wav_file.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.c_int]
     L.zf_encode_wav_memory.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.c_int]
     L.zf_free.argtypes = [vp]
+    L.zf_driver_release_cache.restype = None
     L.zf_free.restype = None
     L.zf_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.zf_host_alloc.restype = C.c_int

@@ -310,6 +310,10 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     // (launched after, or on another stream, it would only get an SM when the persistent kernel ends).
     const bool split_tail = tail && full;
     const uint32_t ring = sl.kev_count % kRing;
+    if (full && !sl.kev[2 * ring]) {  // timing events of the full-frame kernel: created on first use
+        ZF_CUDA(cudaEventCreate(&sl.kev[2 * ring]));
+        ZF_CUDA(cudaEventCreate(&sl.kev[2 * ring + 1]));
+    }
     if (full) ZF_CUDA(cudaEventRecord(sl.kev[2 * ring], s));
     if (split_tail) {
         zf::FrameJob tj = job;
@@ -377,9 +381,18 @@ int ensure_io(zf_encoder *e, Slot &sl) {
     sl.out_cap = frames * e->max_frame_bytes + 64;
     ZF_CUDA(cudaMalloc(&sl.d_pcm, sl.pcm_cap));
     ZF_CUDA(cudaMalloc(&sl.d_out, sl.out_cap));
-    ZF_CUDA(cudaMallocHost(&sl.h_pcm, sl.pcm_cap));
-    ZF_CUDA(cudaMallocHost(&sl.h_out, sl.out_cap));
     sl.have_io = true;
+    return ZF_OK;
+}
+
+// Page-locked staging for callers whose own buffers are pageable; allocated on first need only (page-locking memory is
+// slow -- of the order of a GB/s -- and callers that bring zf_host_alloc buffers never need it).
+int ensure_staging_in(Slot &sl) {
+    if (!sl.h_pcm) ZF_CUDA(cudaMallocHost(&sl.h_pcm, sl.pcm_cap));
+    return ZF_OK;
+}
+int ensure_staging_out(Slot &sl) {
+    if (!sl.h_out) ZF_CUDA(cudaMallocHost(&sl.h_out, sl.out_cap));
     return ZF_OK;
 }
 
@@ -392,7 +405,6 @@ int slot_init(zf_encoder *e, Slot &sl) {
     ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
     ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_up, cudaEventDisableTiming));
     ZF_CUDA(cudaEventCreateWithFlags(&sl.ev_down, cudaEventDisableTiming));
-    for (int i = 0; i < 2 * kRing; i++) ZF_CUDA(cudaEventCreate(&sl.kev[i]));
     ZF_CUDA(cudaMalloc(&sl.d_sizes, sizeof(uint32_t) * frames));
     ZF_CUDA(cudaMalloc(&sl.d_ctl_block, 64 + sizeof(unsigned long long) * frames));
     sl.d_ctl = reinterpret_cast<unsigned int *>(sl.d_ctl_block);
@@ -450,6 +462,8 @@ int slot_submit(zf_encoder *e, Slot &sl, const uint8_t *pcm, uint64_t samples, u
     const size_t bytes = (size_t)samples * e->cfg.channels * (e->cfg.bit_depth / 8);
     const uint8_t *src = pcm;
     if (bytes && !is_pinned_or_device_visible(pcm)) {  // pageable caller memory: stage through pinned
+        rc = ensure_staging_in(sl);
+        if (rc) return rc;
         memcpy(sl.h_pcm, pcm, bytes);
         src = sl.h_pcm;
     }
@@ -506,6 +520,8 @@ int slot_fetch(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *ou
         if (is_pinned_or_device_visible(out)) {
             ZF_CUDA(cudaMemcpyAsync(out, sl.d_out, total, cudaMemcpyDeviceToHost, e->s_down));
         } else {  // pageable caller memory: through the pinned staging buffer, copied on in slot_finish
+            const int rs = ensure_staging_out(sl);
+            if (rs) return rs;
             ZF_CUDA(cudaMemcpyAsync(sl.h_out, sl.d_out, total, cudaMemcpyDeviceToHost, e->s_down));
             sl.copy_dst = out;
             sl.copy_len = total;

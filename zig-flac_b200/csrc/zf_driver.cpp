@@ -77,7 +77,69 @@ struct Sink {
     }
 };
 
-enum : int { kFree = 0, kFilled = 1 };
+// Encoder handles and page-locked chunk buffers are kept between whole-file calls of one process: creating a handle
+// (device buffers, streams, kernel attributes) and page-locking a few hundred MB cost far more than encoding a short
+// file.  Whole-file calls are serialised on `call`; zf_driver_release_cache() gives everything back.
+struct Cache {
+    std::mutex call, mu;
+    struct Enc { zf_config cfg; zf_encoder *h; bool used; };
+    struct Buf { uint8_t *p; size_t cap; bool used; };
+    std::vector<Enc> encs;
+    std::vector<Buf> bufs;
+
+    int encoder(const zf_config &cfg, zf_encoder **out) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (Enc &e : encs)
+                if (!e.used && memcmp(&e.cfg, &cfg, sizeof cfg) == 0) { e.used = true; *out = e.h; return ZF_OK; }
+        }
+        zf_encoder *h = nullptr;
+        const int rc = zf_encoder_create(&cfg, &h);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lk(mu);
+        if (encs.size() >= 16) {  // bounded: drop an idle one
+            for (size_t i = 0; i < encs.size(); i++)
+                if (!encs[i].used) { zf_encoder_destroy(encs[i].h); encs.erase(encs.begin() + (long)i); break; }
+        }
+        encs.push_back({cfg, h, true});
+        *out = h;
+        return ZF_OK;
+    }
+    void put_encoder(zf_encoder *h) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (Enc &e : encs)
+            if (e.h == h) e.used = false;
+    }
+    int buffer(size_t bytes, uint8_t **out) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            Buf *best = nullptr;
+            for (Buf &b : bufs)
+                if (!b.used && b.cap >= bytes && (!best || b.cap < best->cap)) best = &b;
+            if (best) { best->used = true; *out = best->p; return ZF_OK; }
+        }
+        void *p = nullptr;
+        const int rc = zf_host_alloc(bytes, &p);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lk(mu);
+        bufs.push_back({(uint8_t *)p, bytes, true});
+        *out = (uint8_t *)p;
+        return ZF_OK;
+    }
+    void put_buffer(uint8_t *p) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (Buf &b : bufs)
+            if (b.p == p) b.used = false;
+    }
+    void release() {
+        std::lock_guard<std::mutex> lk(mu);
+        for (Enc &e : encs) zf_encoder_destroy(e.h);
+        for (Buf &b : bufs) zf_host_free(b.p);
+        encs.clear();
+        bufs.clear();
+    }
+};
+Cache g_cache;
 
 struct Chunk {
     uint8_t *pcm = nullptr;  // page-locked
@@ -107,6 +169,7 @@ struct Pipe {
 };
 
 int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t want_samples, const int *devices, int n_devices) {
+    std::lock_guard<std::mutex> one_call(g_cache.call);
     const size_t ic_bytes = (size_t)fmt.channels * fmt.bytes_per_sample;
     const uint64_t want_frames = (want_samples + kFrameSize - 1) / kFrameSize;
     int one = 0;
@@ -126,14 +189,11 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
     Pipe pipe;
     pipe.ring.resize((size_t)ring_n);
     auto release = [&] {
-        for (Chunk &c : pipe.ring) { zf_host_free(c.pcm); zf_host_free(c.out); }
+        for (Chunk &c : pipe.ring) { if (c.pcm) g_cache.put_buffer(c.pcm); if (c.out) g_cache.put_buffer(c.out); }
     };
     for (Chunk &c : pipe.ring) {
-        void *a = nullptr, *b = nullptr;
-        int rc = zf_host_alloc(chunk_bytes, &a);
-        if (!rc) rc = zf_host_alloc(out_cap, &b);
-        c.pcm = (uint8_t *)a;
-        c.out = (uint8_t *)b;
+        int rc = g_cache.buffer(chunk_bytes, &c.pcm);
+        if (!rc) rc = g_cache.buffer(out_cap, &c.out);
         if (rc) { release(); return rc; }
         c.sizes.resize(chunk_frames);
     }
@@ -214,7 +274,7 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
             zf_config dc = cfg;
             dc.device_id = devices[g];
             zf_encoder *enc = nullptr;
-            int rc = zf_encoder_create(&dc, &enc);
+            int rc = g_cache.encoder(dc, &enc);
             if (rc) { pipe.fail(rc); return; }
             for (long long k = g;; k += n_devices) {
                 Chunk &c = pipe.ring[(size_t)(k % ring_n)];
@@ -231,7 +291,7 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
                 c.encoded = true;
                 pipe.cv.notify_all();
             }
-            zf_encoder_destroy(enc);
+            g_cache.put_encoder(enc);
         });
     }
 
@@ -346,5 +406,10 @@ int zf_encode_wav_file(const char *in_path, const char *out_path, const int *dev
 }
 
 void zf_free(void *p) { free(p); }
+
+void zf_driver_release_cache(void) {
+    std::lock_guard<std::mutex> one_call(g_cache.call);
+    g_cache.release();
+}
 
 }  // extern "C"
