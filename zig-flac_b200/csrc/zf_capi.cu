@@ -357,7 +357,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         (*launches)++;
     }
     if (split_tail) {
-        zf::zf_append_tail_kernel<<<1, 256, 0, s>>>(sl.d_tail, reinterpret_cast<const uint32_t *>(sl.d_tail_meta + 2), d_out,
+        zf::zf_append_tail_kernel<<<1, 512, 0, s>>>(sl.d_tail, reinterpret_cast<const uint32_t *>(sl.d_tail_meta + 2), d_out,
                                                     out_cap, d_total, d_sizes, (uint32_t)full, sl.d_ctl + 2);
         (*launches)++;
     } else if (tail) {  // a stream shorter than one block: the short frame is the whole batch

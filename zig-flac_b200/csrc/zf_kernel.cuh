@@ -1262,8 +1262,19 @@ __global__ void zf_append_tail_kernel(const uint8_t *tail, const uint32_t *tail_
     const uint32_t size = *tail_size;
     const unsigned long long off = *total;
     const bool fits = off + size <= out_cap;  // like every frame: one that does not fit is counted, not written
-    if (fits)
-        for (uint32_t k = threadIdx.x; k < size; k += blockDim.x) out[off + k] = tail[k];
+    if (fits) {
+        // 16 source bytes per thread and trip (the private buffer is aligned; the destination is wherever the stream ends)
+        const uint4 *t16 = reinterpret_cast<const uint4 *>(tail);
+        uint8_t *dst = out + off;
+        for (uint32_t k = threadIdx.x; 16u * k < size; k += blockDim.x) {
+            const uint4 v = t16[k];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t left = size - 16u * k;
+#pragma unroll
+            for (uint32_t b = 0; b < 16; b++)
+                if (b < left) dst[16u * k + b] = (uint8_t)(w[b >> 2] >> (8u * (b & 3u)));
+        }
+    }
     __syncthreads();  // every thread has read *total
     if (threadIdx.x == 0) {
         if (!fits) atomicOr(status, kStatusOutOverflow);
