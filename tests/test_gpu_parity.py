@@ -327,3 +327,59 @@ def test_patchwork_stream_many_frames_per_cta(zf, oracle, bits):
             assert ref.tobytes() == got.tobytes()
     finally:
         enc.close()
+
+
+def _random_stream(rng, n, channels, bits):
+    F = 1 << (bits - 1)
+    planes = []
+    for c in range(channels):
+        kind = int(rng.integers(0, 7))
+        t = np.arange(n)
+        amp = float(F) * 10.0 ** float(rng.uniform(-4, 0))
+        if kind == 0:
+            v = np.zeros(n)
+        elif kind == 1:
+            v = np.full(n, float(rng.integers(-F, F)))
+        elif kind == 2:
+            v = amp * 0.9 * np.sin(t * rng.uniform(0.001, 1.5) + rng.uniform(0, 6))
+        elif kind == 3:
+            v = rng.integers(-F, F, n).astype(np.float64)
+        elif kind == 4:
+            v = rng.normal(0, amp / 4, n)
+        elif kind == 5:
+            sh = int(rng.integers(1, bits - 1))
+            v = ((rng.integers(-F, F, n) >> sh) << sh).astype(np.float64)
+        else:
+            v = np.cumsum(rng.integers(-5, 6, n)).astype(np.float64)
+        planes.append(np.clip(v.astype(np.int64), -F, F - 1))
+    if channels == 2 and rng.random() < 0.3:
+        planes[1] = np.clip(planes[0] + rng.integers(-3, 4, n), -F, F - 1)  # correlated pair: the side channel wins
+    return planes
+
+
+def test_random_configurations(zf, oracle):
+    """Randomised sweep over what Encoder.Config can express (encoder.zig:609-656): block size, channels, depth, Rice
+    limits, decorrelation, sample rate, stream length (any tail), first frame number -- every stream byte-identical to
+    the oracle.  Seeded: a failure prints its case."""
+    rng = np.random.default_rng(20250)
+    for case in range(160):
+        bits = int(rng.choice([16, 24, 32]))
+        channels = int(rng.choice([1, 2, 2, 2, 3, 6]))
+        block = int(rng.choice([4096, 4096, 4096, 2048, 1024, 576, 192, 1000, 4000, 16, 64]))
+        mro = int(rng.choice([8, 8, 8, 0, 3, 6]))
+        mrp = int(rng.choice([30, 30, 14, 1, 7, 20]))
+        dec = bool(rng.random() < 0.85)
+        rate = int(rng.choice([44100, 48000, 96000, 192000, 8000, 12345, 200, 100000]))
+        frames = int(rng.integers(1, 5))
+        n = block * (frames - 1) + int(rng.integers(1, block + 1))
+        first = int(rng.choice([0, 0, 127, 2047, 65535, (1 << 21) - 1]))
+        planes = _random_stream(rng, n, channels, bits)
+        pcm = oracle.pcm_bytes_from_int(signals.interleave(planes), bits)
+        what = dict(case=case, bits=bits, channels=channels, block=block, mro=mro, mrp=mrp, dec=dec, rate=rate, n=n, first=first)
+        cfg = oracle.config(channels, bits, block_size=block, stereo_decorrelation=int(dec), max_rice_order=mro, max_rice_param=mrp)
+        ref, rs = oracle.encode_pcm(pcm, n, cfg, rate, first)
+        with zf.Encoder(zf.Config(channels, bits, block_size=block, stereo_decorrelation=dec, max_rice_order=mro,
+                                  max_rice_param=mrp), rate, max_frames_per_batch=3) as enc:
+            got, gs = enc.encode_pcm(pcm, n, first)
+        assert np.array_equal(rs, gs), what
+        assert ref.tobytes() == got.tobytes(), what

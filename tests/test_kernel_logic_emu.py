@@ -293,3 +293,20 @@ def test_v3_kernel_any_rice_limit_and_sample_rate(emu, oracle, bits):
         _check(emu, oracle, pcm, n, bits, rate=rate, first=(1 << 21) + 3)
         _check(emu, oracle, pcm, n, bits, rate=rate, first=5)
     assert emu.emu_v3_frames() - before == 2 * (7 + 18)
+
+
+def test_random_configurations_emulated(emu, oracle):
+    """A short randomised sweep over block sizes / tails / Rice limits through the emulated kernels (the long one runs on
+    the GPU: tests/test_gpu_parity.py::test_random_configurations)."""
+    rng = np.random.default_rng(77)
+    for case in range(40):
+        bits = int(rng.choice([16, 24, 32]))
+        channels = int(rng.choice([1, 2, 2, 3]))
+        block = int(rng.choice([4096, 2048, 1024, 576, 192, 1000, 4000, 16, 64, 4080, 255 * 8]))
+        mro = int(rng.choice([8, 8, 0, 3, 6]))
+        mrp = int(rng.choice([30, 14, 1, 7]))
+        n = block + int(rng.integers(1, block + 1))
+        F = 1 << (bits - 1)
+        planes = [np.clip((rng.normal(0, F * 10.0 ** rng.uniform(-4, -0.5), n)).astype(np.int64), -F, F - 1) for _ in range(channels)]
+        pcm = oracle.pcm_bytes_from_int(signals.interleave(planes), bits)
+        _check(emu, oracle, pcm, n, bits, channels=channels, block=block, mro=mro, mrp=mrp, rate=48000)

@@ -191,12 +191,9 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
     auto release = [&] {
         for (Chunk &c : pipe.ring) { if (c.pcm) g_cache.put_buffer(c.pcm); if (c.out) g_cache.put_buffer(c.out); }
     };
-    for (Chunk &c : pipe.ring) {
-        int rc = g_cache.buffer(chunk_bytes, &c.pcm);
-        if (!rc) rc = g_cache.buffer(out_cap, &c.out);
-        if (rc) { release(); return rc; }
-        c.sizes.resize(chunk_frames);
-    }
+    // the ring's page-locked buffers are taken (from the cache, or page-locked now) by the reader thread as it first fills
+    // each slot: page-locking runs at a GB/s or two, and this way it overlaps the MD5 of the chunks already read
+    for (Chunk &c : pipe.ring) c.sizes.resize(chunk_frames);
 
     // ---- reader (+ MD5 of one-byte streams: their raw bytes are converted in place, so they are hashed first) ----
     const bool one_byte = fmt.bytes_per_sample == 1;
@@ -213,6 +210,11 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
                 std::unique_lock<std::mutex> lk(pipe.mu);
                 pipe.cv.wait(lk, [&] { return pipe.rc != ZF_OK || c.index < 0; });
                 if (pipe.rc != ZF_OK) return;
+            }
+            if (!c.pcm) {
+                int rc = g_cache.buffer(chunk_bytes, &c.pcm);
+                if (!rc) rc = g_cache.buffer(out_cap, &c.out);
+                if (rc) { pipe.fail(rc); return; }
             }
             const uint64_t ask = std::min<uint64_t>(left, (uint64_t)chunk_frames * kFrameSize);
             size_t got = ask ? src.read(c.pcm, (size_t)ask * ic_bytes) : 0;

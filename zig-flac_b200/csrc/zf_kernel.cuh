@@ -825,52 +825,106 @@ ZF_DEVICE void block_scan2(SmemCommon &c, int t, uint32_t a, uint32_t b, uint32_
 // nslots candidate channels are processed together to share the barriers.
 // ---------------------------------------------------------------------------------------------------
 
+// One (partition, abs-sum, width) contribution per lane (part == 0xffffffff: none): the warp adds up the contributions of
+// every partition its lanes name and issues ONE atomic pair per partition.  (Per-sample 64-bit shared-memory atomics -- a
+// CAS loop, thirty-two lanes on one address -- were half of the one-CTA last-frame launch: 128 us for 4080 samples.)
+ZF_DEVICE void warp_leaf_add(SmemCommon &c, uint32_t slot, uint32_t leaf0, uint32_t part, unsigned long long sum, uint32_t width,
+                             int lane) {
+    uint32_t pending = __ballot_sync(0xffffffffu, part != 0xffffffffu);
+    while (pending) {  // warp-uniform
+        const int src = (int)ctz32(pending);
+        const uint32_t p = __shfl_sync(0xffffffffu, part, src);
+        const bool in = part == p;
+        const unsigned long long s = warp_sum(in ? sum : 0ull);
+        const uint32_t w = reduce_max(in ? width : 0u);
+        if (lane == src) {
+            atomicAdd(&c.psum[slot][leaf0 + p], s);
+            atomicMax(&c.pbits[slot][leaf0 + p], w);
+        }
+        pending &= ~__ballot_sync(0xffffffffu, in);
+    }
+}
+
+// rice.calcSums leaves (rice.zig:288-340) of this thread's residuals r[j] (sample base + j; entries below the order or
+// beyond n are ignored).  Partitions of exactly one thread are stored directly; otherwise a thread's samples are
+// grouped into runs of one partition each (at most two when a partition holds eight samples or more) and the runs go
+// through warp_leaf_add; partitions smaller than a thread (tiny frames only) fall back to per-sample atomics.
+template <bool FULL>
+ZF_DEVICE void rice_leaves_from(SmemCommon &c, uint32_t slot, const int32_t (&r)[kSpt], int t, uint32_t base, uint32_t n) {
+    const SlotDec &d = c.dec[slot];
+    const uint32_t order = d.order, mpo = d.mpo;
+    const uint32_t psz = n >> mpo;
+    const uint32_t leaf0 = (1u << mpo) - 1u;
+    const int lane = t & 31;
+    if (FULL || psz == (uint32_t)kSpt) {  // (FULL: 4096 samples, mpo 8 unless max_rice_order is lower -- then psz is a multiple of 8)
+        if (psz == (uint32_t)kSpt) {
+            unsigned long long sum = 0;
+            int32_t mn = 0, mx = 0;
+#pragma unroll
+            for (int j = 0; j < kSpt; j++) {
+                const uint32_t i = base + j;
+                if ((FULL || i < n) && i >= order) {
+                    sum += uabs(r[j]);
+                    mn = r[j] < mn ? r[j] : mn;
+                    mx = r[j] > mx ? r[j] : mx;
+                }
+            }
+            const uint32_t zm = zigzag(mn), zx = zigzag(mx);
+            if (FULL || base < n) {
+                const uint32_t part = FULL ? (base >> (12u - mpo)) : base / psz;
+                c.psum[slot][leaf0 + part] = sum;
+                c.pbits[slot][leaf0 + part] = bitlen32(zm > zx ? zm : zx);  // bit length of the OR of the zigzags
+            }
+            return;
+        }
+    }
+    if (psz >= (uint32_t)kSpt) {
+        // at most two runs per thread
+        uint32_t part[2] = {0xffffffffu, 0xffffffffu};
+        unsigned long long sum[2] = {0, 0};
+        int32_t mn[2] = {0, 0}, mx[2] = {0, 0};
+        const uint32_t p0 = base < n ? base / psz : 0u;
+        const uint32_t bound = (p0 + 1u) * psz;  // first sample of the next partition
+#pragma unroll
+        for (int j = 0; j < kSpt; j++) {
+            const uint32_t i = base + j;
+            if (i < n) {
+                const uint32_t k = i >= bound ? 1u : 0u;
+                part[k] = p0 + k;
+                if (i >= order) {
+                    sum[k] += uabs(r[j]);
+                    mn[k] = r[j] < mn[k] ? r[j] : mn[k];
+                    mx[k] = r[j] > mx[k] ? r[j] : mx[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t zm = zigzag(mn[k]), zx = zigzag(mx[k]);
+            warp_leaf_add(c, slot, leaf0, part[k], sum[k], bitlen32(zm > zx ? zm : zx), lane);
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < kSpt; j++) {
+        const uint32_t i = base + j;
+        if (i < n && i >= order) {
+            const uint32_t part = i / psz;
+            atomicAdd(&c.psum[slot][leaf0 + part], (unsigned long long)uabs(r[j]));
+            atomicMax(&c.pbits[slot][leaf0 + part], bitlen32(zigzag(r[j])));
+        }
+    }
+}
+
 template <bool WIDE, bool FULL>
 ZF_DEVICE void rice_leaves(SmemCommon &c, uint32_t slot, const typename Ar<WIDE>::T (&x)[kX], int t, uint32_t base,
                            uint32_t n) {
     typedef typename Ar<WIDE>::T T;
     const SlotDec &d = c.dec[slot];
-    const uint32_t order = d.order, waste = d.waste, mpo = d.mpo;
-    const uint32_t psz = n >> mpo;
-    const uint32_t leaf0 = (1u << mpo) - 1u;
-    const bool chunked = FULL || ((psz & (kSpt - 1)) == 0);
-    if (chunked) {
-        unsigned long long sum = 0;
-        int32_t mn = 0, mx = 0;
+    int32_t r[kSpt];
 #pragma unroll
-        for (int j = 0; j < kSpt; j++) {
-            const uint32_t i = base + j;
-            if ((FULL || i < n) && i >= order) {
-                const int32_t r = (int32_t)(fixed_residual<T>(x, order, j) >> waste);
-                sum += uabs(r);
-                mn = r < mn ? r : mn;
-                mx = r > mx ? r : mx;
-            }
-        }
-        const uint32_t zm = zigzag(mn), zx = zigzag(mx);
-        const uint32_t width = bitlen32(zm > zx ? zm : zx);  // bit length of OR of zigzags == max signed width
-        if (FULL || base < n) {
-            const uint32_t part = FULL ? (base >> (12u - mpo)) : base / psz;
-            if (psz == (uint32_t)kSpt) {
-                c.psum[slot][leaf0 + part] = sum;
-                c.pbits[slot][leaf0 + part] = width;
-            } else {
-                atomicAdd(&c.psum[slot][leaf0 + part], sum);
-                atomicMax(&c.pbits[slot][leaf0 + part], width);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kSpt; j++) {
-            const uint32_t i = base + j;
-            if (i < n && i >= order) {
-                const int32_t r = (int32_t)(fixed_residual<T>(x, order, j) >> waste);
-                const uint32_t part = i / psz;
-                atomicAdd(&c.psum[slot][leaf0 + part], (unsigned long long)uabs(r));
-                atomicMax(&c.pbits[slot][leaf0 + part], bitlen32(zigzag(r)));
-            }
-        }
-    }
+    for (int j = 0; j < kSpt; j++) r[j] = (int32_t)(fixed_residual<T>(x, d.order, j) >> d.waste);
+    rice_leaves_from<FULL>(c, slot, r, t, base, n);
 }
 
 // zero the leaves that rice_leaves accumulates into with atomics

@@ -164,44 +164,6 @@ ZF_DEVICE bool lpc_residual8(const int32_t *plane, const Model &m, uint32_t base
     return ok;
 }
 
-// rice.calcSums leaves (rice.zig:288-340) from residuals held in registers; same geometry rules as rice_leaves()
-ZF_DEVICE void rice_leaves_r(SmemCommon &c, uint32_t slot, const int32_t (&r)[kSpt], uint32_t base, uint32_t n) {
-    const SlotDec &d = c.dec[slot];
-    const uint32_t order = d.order, mpo = d.mpo;
-    const uint32_t psz = n >> mpo;
-    const uint32_t leaf0 = (1u << mpo) - 1u;
-    if ((psz & (kSpt - 1)) == 0) {
-        unsigned long long sum = 0;
-        int32_t mn = 0, mx = 0;
-#pragma unroll
-        for (int j = 0; j < kSpt; j++) {
-            const uint32_t i = base + j;
-            if (i < n && i >= order) {
-                sum += uabs(r[j]);
-                mn = r[j] < mn ? r[j] : mn;
-                mx = r[j] > mx ? r[j] : mx;
-            }
-        }
-        const uint32_t zm = zigzag(mn), zx = zigzag(mx);
-        const uint32_t width = bitlen32(zm > zx ? zm : zx);
-        if (base < n) {
-            const uint32_t part = base / psz;
-            atomicAdd(&c.psum[slot][leaf0 + part], sum);
-            atomicMax(&c.pbits[slot][leaf0 + part], width);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kSpt; j++) {
-            const uint32_t i = base + j;
-            if (i < n && i >= order) {
-                const uint32_t part = i / psz;
-                atomicAdd(&c.psum[slot][leaf0 + part], (unsigned long long)uabs(r[j]));
-                atomicMax(&c.pbits[slot][leaf0 + part], bitlen32(zigzag(r[j])));
-            }
-        }
-    }
-}
-
 // SUBFRAME_LPC: header 1xxxxx with order - 1 (+ wasted-bits flag and unary count), warm-ups, 4-bit precision - 1, 5-bit
 // shift, coefficients, then the residual exactly as in a FIXED subframe (frame_writer.zig:328-361).  MODE 0 counts.
 template <int MODE>
@@ -422,12 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) zf_encode_stereo_lpc_kernel(const
                 c.dec[t] = d;
             }
             __syncthreads();
-            for (uint32_t s = 0; s < 4; s++) {  // LPC leaves accumulate with atomics
-                const SlotDec &d = c.dec[s];
-                if (d.kind != kFixed) continue;
-                const uint32_t leaf0 = (1u << d.mpo) - 1u, cnt = 1u << d.mpo;
-                for (uint32_t j = t; j < cnt; j += kThreads) { c.psum[s][leaf0 + j] = 0; c.pbits[s][leaf0 + j] = 0; }
-            }
+            for (uint32_t s = 0; s < 4; s++) rice_zero_leaves(c, s, t, n);  // leaves that accumulate
             __syncthreads();
 #pragma unroll 1
             for (uint32_t s = 0; s < 4; s++) {
@@ -439,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) zf_encode_stereo_lpc_kernel(const
                 __syncthreads();
                 int32_t r[kSpt];
                 if (!lpc_residual8(sm.plane, sm.model[s], base, n, r)) atomicOr(&sm.bad[s], 1u);
-                rice_leaves_r(c, s, r, base, n);
+                rice_leaves_from<false>(c, s, r, t, base, n);
                 __syncthreads();
             }
             rice_tree_and_search(c, t, n, 4);
