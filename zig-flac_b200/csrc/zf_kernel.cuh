@@ -744,8 +744,10 @@ ZF_DEVICE uint32_t emit_subframe(const typename Ar<WIDE>::T (&x)[kX], int t, uin
     const bool uniform = FULL || ((psz & (kSpt - 1)) == 0);
     uint32_t choice = 0;
     bool at_start = false;
-    if (uniform && (FULL || base < n)) {
-        const uint32_t part = FULL ? (base >> (12u - d.po)) : base / psz;
+    uint32_t part = 0, next = 0;  // partition of the sample in hand, first sample of the one behind it
+    if (FULL || base < n) {
+        part = FULL ? (base >> (12u - d.po)) : base / psz;
+        next = (part + 1u) * psz;
         choice = choice_row[part];
         at_start = (base - part * psz) == 0;
     }
@@ -754,10 +756,13 @@ ZF_DEVICE uint32_t emit_subframe(const typename Ar<WIDE>::T (&x)[kX], int t, uin
         const uint32_t i = base + j;
         if (FULL || i < n) {
             bool hdr_here = at_start && j == 0;
-            if (!uniform) {
-                const uint32_t part = i / psz;
-                choice = choice_row[part];
-                hdr_here = (i - part * psz) == 0;
+            if (!uniform && j > 0) {  // partitions that are not whole numbers of threads: step over the boundary
+                hdr_here = i >= next;
+                if (hdr_here) {
+                    part++;
+                    next += psz;
+                    choice = choice_row[part];
+                }
             }
             const bool esc = (choice & 0x80u) != 0;
             if (hdr_here) {  // partition header: parameter, or escape code + 5-bit width (:341-357)
@@ -980,10 +985,16 @@ ZF_DEVICE void rice_tree_and_search(SmemCommon &c, int t, uint32_t n, uint32_t n
             }
             const bool five = act && choice < 0x80u && choice > 14u;  // isRice2, rice.zig:74-76
             if (m0 == 0 && t < 32) {
-                // warp 0 of the first round holds levels 0..4 mixed
-                if (act) {
-                    atomicAdd(&c.levelcost[s][lvl], cost);
-                    if (five) atomicOr(&c.levelfive[s], 1u << lvl);
+                // warp 0 of the first round holds levels 0..4 mixed: one masked warp sum per level (nobody else touches
+                // these levels; 64-bit shared-memory atomics are CAS loops)
+#pragma unroll 1
+                for (uint32_t q = 0; q < 5; q++) {
+                    const unsigned long long ws = warp_sum((act && lvl == q) ? cost : 0ull);
+                    const uint32_t wf = reduce_or((five && lvl == q) ? 1u : 0u);
+                    if (lane == 0 && q <= d.mpo) {
+                        c.levelcost[s][q] += ws;
+                        if (wf) atomicOr(&c.levelfive[s], 1u << q);
+                    }
                 }
             } else {
                 // whole warp is in one level (or entirely inactive)

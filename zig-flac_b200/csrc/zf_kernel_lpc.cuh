@@ -199,14 +199,15 @@ ZF_DEVICE uint32_t emit_lpc(const int32_t (&r)[kSpt], const long long *warm, con
         if (MODE == 1) bw.put(pos, (d.method << 4) | d.po, 6);
         pos += 6;
     }
+    uint32_t part = base < n ? base / psz : 0u, next = (part + 1u) * psz;
 #pragma unroll
     for (int j = 0; j < kSpt; j++) {
         const uint32_t i = base + j;
         if (i < n) {
-            const uint32_t part = i / psz;
+            if (i >= next) { part++; next += psz; }
             const uint32_t choice = choice_row[part];
             const bool esc = (choice & 0x80u) != 0;
-            if (i - part * psz == 0) {
+            if (i == next - psz) {
                 if (MODE == 1) {
                     if (esc) {
                         bw.put(pos, esc_code, param_len);

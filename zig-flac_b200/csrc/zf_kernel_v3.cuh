@@ -1379,16 +1379,12 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         }
         // round 2 of the look-back, if round 1 did not reach a prefix: its window has arrived during pass 2
         if (P.valid && warp == kW - 1 && !sm.lb_done) lb_step(sm, lba, lane, P);
-        __syncwarp();  // this warp's tree nodes (levels 7..3 of its own 32 leaves) are in shared memory
-        // ================= round B, part 1: heap levels 3..7 stay inside the warp =================
-        // A warp's 32 leaves form a subtree of 31 inner nodes (one of level 3, two of level 4, .. sixteen of level 7):
-        // lane l = 1..31 is local heap node l.  No block barrier between the tree and its search.
+        __syncthreads();
+        // ================= round B: heap nodes 1..255 (levels 0..7), one per thread =================
         {
-            const uint32_t l = (uint32_t)lane;
-            const uint32_t ll = l ? floor_log2(l) : 0u;  // 0..4
-            const uint32_t lvl = 3u + ll;
-            const uint32_t j = ((uint32_t)warp << ll) + (l - (1u << ll));
-            const uint32_t m = (1u << lvl) + j;
+            const uint32_t m = (uint32_t)t;
+            const uint32_t lvl = m ? floor_log2(m) : 0u;
+            const uint32_t j = m - (1u << lvl);
             // every candidate, FIXED or not (what a CONSTANT / VERBATIM candidate yields is never looked at): without the
             // early exit two candidates' dependent chains interleave
 #pragma unroll 2
@@ -1397,10 +1393,29 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 uint32_t choice = 0, cost = 0;
                 unsigned long long S = 0;
                 uint32_t B = 0;
-                if (l >= 1) {
-                    const unsigned long long v = sc.node[s][m];
-                    S = v & 0xffffffffffffull;
-                    B = (uint32_t)(v >> 48);
+                if (m >= 1) {
+                    if (lvl < 3) {  // levels 2..0 straight from the eight level-3 nodes (heap 8..15): all eight are
+                                    // loaded (independent, broadcast) and the ones of this node's span are kept
+                        const ulonglong2 *np = reinterpret_cast<const ulonglong2 *>(&sc.node[s][8]);
+                        unsigned long long nv[8];
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const ulonglong2 v2 = np[k];
+                            nv[2 * k] = v2.x;
+                            nv[2 * k + 1] = v2.y;
+                        }
+#pragma unroll
+                        for (uint32_t k = 0; k < 8; k++) {
+                            const bool in = (k >> (3u - lvl)) == j;
+                            S += in ? (nv[k] & 0xffffffffffffull) : 0ull;
+                            const uint32_t b = in ? (uint32_t)(nv[k] >> 48) : 0u;
+                            B = b > B ? b : B;
+                        }
+                    } else {
+                        const unsigned long long v = sc.node[s][m];
+                        S = v & 0xffffffffffffull;
+                        B = (uint32_t)(v >> 48);
+                    }
                 }
                 const uint32_t cnt = ((uint32_t)kN >> lvl) - (j == 0 ? d.order : 0u);  // rice.zig:356,371
                 if constexpr (WIDE) {
@@ -1409,22 +1424,22 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                     if (__builtin_expect(__any_sync(0xffffffffu, (S >> 32) != 0), 0)) best_param_nw(S, B, cnt, d.P, choice, cost);
                     else best_param_32((uint32_t)S, B, cnt, d.P, choice, cost);
                 }
-                if (l >= 1) sm.choice[s][m] = (uint8_t)choice;
+                if (m >= 1) sm.choice[s][m] = (uint8_t)choice;
                 else cost = 0;
-                const bool five = l >= 1 && choice < 0x80u && choice > 14u;  // isRice2, rice.zig:74-76
+                const bool five = m >= 1 && choice < 0x80u && choice > 14u;  // isRice2, rice.zig:74-76
                 const uint32_t fm = __ballot_sync(0xffffffffu, five);
-                // cost of the warp's nodes per level: lanes [2^q, 2^(q+1)) are level 3 + q -- an aligned group, so a
-                // butterfly that stops at the group's size leaves the level's sum in the group's first lane
-                uint32_t acc = cost;
-#pragma unroll
-                for (uint32_t k = 0; k < 4; k++) {
-                    const uint32_t o = __shfl_xor_sync(0xffffffffu, acc, 1 << k);
-                    if (k < ll) acc += o;
-                }
-                if (l >= 1 && (l & (l - 1u)) == 0) {  // lanes 1, 2, 4, 8, 16
-                    sm.lvlcost[s][lvl][warp] = acc;
-                    const uint32_t group = ((1u << (1u << ll)) - 1u) << (1u << ll);  // the level's lanes
-                    sm.lvlfive[s][lvl][warp] = (fm & group) ? 1 : 0;
+                if (warp == 0) {  // heap nodes 1..31: levels 0..4 -- each node's cost is one partial of its level
+                    if (m >= 1) {
+                        sm.lvlcost[s][lvl][j] = cost;
+                        sm.lvlfive[s][lvl][j] = five ? 1 : 0;
+                    }
+                } else {  // warp 1: level 5; warps 2-3: level 6; warps 4-7: level 7
+                    const uint32_t wsum = reduce_add(cost);
+                    const uint32_t wl = floor_log2((uint32_t)warp);
+                    if (lane == 0) {
+                        sm.lvlcost[s][5u + wl][(uint32_t)warp - (1u << wl)] = wsum;
+                        sm.lvlfive[s][5u + wl][(uint32_t)warp - (1u << wl)] = fm ? 1 : 0;
+                    }
                 }
             }
         }
@@ -1432,49 +1447,6 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             while (!sm.lb_done) lb_step(sm, lba, lane, P);
         }
         __syncthreads();
-        // ================= round B, part 2: heap levels 0..2 (seven nodes per candidate), in every warp =================
-        // They need the eight level-3 nodes of all warps.  Every warp works them out for itself (28 lanes) and writes the
-        // same values to the same places, so that the pick below needs no further barrier.
-        {
-            const uint32_t s = (uint32_t)lane / 7u, mm = 1u + (uint32_t)lane % 7u;  // lanes 28..31 idle
-            const uint32_t lvl = floor_log2(mm);
-            const uint32_t j = mm - (1u << lvl);
-            const bool act = lane < 28;
-            const Dec &d = sm.dec[act ? s : 0u];
-            uint32_t choice = 0, cost = 0;
-            unsigned long long S = 0;
-            uint32_t B = 0;
-            {
-                const ulonglong2 *np = reinterpret_cast<const ulonglong2 *>(&sc.node[act ? s : 0u][8]);
-                unsigned long long nv[8];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const ulonglong2 v2 = np[k];
-                    nv[2 * k] = v2.x;
-                    nv[2 * k + 1] = v2.y;
-                }
-#pragma unroll
-                for (uint32_t k = 0; k < 8; k++) {
-                    const bool in = (k >> (3u - lvl)) == j;
-                    S += in ? (nv[k] & 0xffffffffffffull) : 0ull;
-                    const uint32_t b = in ? (uint32_t)(nv[k] >> 48) : 0u;
-                    B = b > B ? b : B;
-                }
-            }
-            const uint32_t cnt = ((uint32_t)kN >> lvl) - (j == 0 ? d.order : 0u);
-            if constexpr (WIDE) {
-                best_param_w(S, B, cnt, d.P, choice, cost);
-            } else {
-                if (__builtin_expect(__any_sync(0xffffffffu, (S >> 32) != 0), 0)) best_param_nw(S, B, cnt, d.P, choice, cost);
-                else best_param_32((uint32_t)S, B, cnt, d.P, choice, cost);
-            }
-            if (act) {
-                sm.choice[s][mm] = (uint8_t)choice;
-                sm.lvlcost[s][lvl][j] = cost;
-                sm.lvlfive[s][lvl][j] = (choice < 0x80u && choice > 14u) ? 1 : 0;
-            }
-            __syncwarp();
-        }
         // the previous frame leaves the bit buffer (the scan's barrier orders these reads before the next stores; the
         // buffer is not cleared: see below)
         if (P.valid) copy_out(sm, job.out, job.out_cap, t, P);
