@@ -368,50 +368,54 @@ def main():
     # ---- whole file: WAV bytes -> FLAC bytes through zf_encode_wav_memory (what `flac in.wav out.flac` does after the read:
     #      parse, MD5 of the PCM on a host thread, chunked encode, STREAMINFO back-patch); the serial MD5 bounds it ----
     e2e_file = None
-    if world == 1 and not args.no_e2e_file and pcm_bytes < (1 << 32) - 64:
-        import struct
-        fmt_chunk = struct.pack("<HHIIHH", 1, CHANNELS, rate, rate * ic_bytes, ic_bytes, bits)
-        head = b"RIFF" + struct.pack("<I", 4 + 8 + len(fmt_chunk) + 8 + pcm_bytes) + b"WAVE" + b"fmt " + \
-            struct.pack("<I", len(fmt_chunk)) + fmt_chunk + b"data" + struct.pack("<I", pcm_bytes)
-        wav = np.empty(len(head) + pcm_bytes, dtype=np.uint8)
-        wav[:len(head)] = np.frombuffer(head, dtype=np.uint8)
-        wav[len(head):] = h_pcm_np
-        if LPC_ORDER.get(args.workload, 0) == 0:  # the driver mirrors the reference CLI: Config.default, no LPC
-            rc, flac = zf.wav_to_flac(wav, devices=[local_rank])  # warm-up (page-locks its chunk buffers)
-            file_steps = 2
-            t0 = time.perf_counter()
-            for _ in range(file_steps):
-                rc, flac = zf.wav_to_flac(wav, devices=[local_rank])
-            file_s = (time.perf_counter() - t0) / file_steps
-            md5 = zf.Md5()
-            t0 = time.perf_counter()
-            md5.update(h_pcm_np)
-            digest = md5.final()
-            md5_s = time.perf_counter() - t0
-            e2e_file = {"value": round(nsamples * CHANNELS / file_s / 1e6, 2), "unit": UNIT, "ms_per_file": round(file_s * 1e3, 2),
-                        "md5_only_ms": round(md5_s * 1e3, 2), "flac_bytes": len(flac) if flac else None, "status": rc,
-                        "md5_matches_streaminfo": bool(flac and flac[26:42] == digest),
-                        "api": "zf_encode_wav_memory (reader | MD5 thread | encoder | writer pipeline over 2048-frame chunks)",
-                        "note": "warm library call; bounded by the serial MD5 of the PCM (md5_only_ms), which the reference computes too"}
-            # ... and the CLI as a user runs it: a fresh process (CUDA context creation included), files on tmpfs
-            cli = os.path.join(ROOT, "zig-flac_b200", "flac")
-            shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-            if os.path.exists(cli):
-                import subprocess
-                fin, fout = os.path.join(shm, f"zf_bench_{os.getpid()}.wav"), os.path.join(shm, f"zf_bench_{os.getpid()}.flac")
-                try:
-                    wav.tofile(fin)
-                    t0 = time.perf_counter()
-                    r = subprocess.run([cli, fin, fout], capture_output=True)
-                    cli_s = time.perf_counter() - t0
-                    same_file = r.returncode == 0 and flac is not None and open(fout, "rb").read() == flac
-                    e2e_file["cli"] = {"wall_ms": round(cli_s * 1e3, 1), "exit": r.returncode, "same_bytes_as_library": bool(same_file),
-                                       "note": "`flac in.wav out.flac` in a fresh process: process start, CUDA context, file I/O on tmpfs included"}
-                finally:
-                    for f in (fin, fout):
-                        if os.path.exists(f):
-                            os.remove(f)
-        del wav
+    try:
+        if world == 1 and not args.no_e2e_file and pcm_bytes < (1 << 32) - 64:
+            import struct
+            fmt_chunk = struct.pack("<HHIIHH", 1, CHANNELS, rate, rate * ic_bytes, ic_bytes, bits)
+            head = b"RIFF" + struct.pack("<I", 4 + 8 + len(fmt_chunk) + 8 + pcm_bytes) + b"WAVE" + b"fmt " + \
+                struct.pack("<I", len(fmt_chunk)) + fmt_chunk + b"data" + struct.pack("<I", pcm_bytes)
+            wav = np.empty(len(head) + pcm_bytes, dtype=np.uint8)
+            wav[:len(head)] = np.frombuffer(head, dtype=np.uint8)
+            wav[len(head):] = h_pcm_np
+            if LPC_ORDER.get(args.workload, 0) == 0:  # the driver mirrors the reference CLI: Config.default, no LPC
+                rc, flac = zf.wav_to_flac(wav, devices=[local_rank])  # warm-up (page-locks its chunk buffers)
+                file_steps = 2
+                t0 = time.perf_counter()
+                for _ in range(file_steps):
+                    rc, flac = zf.wav_to_flac(wav, devices=[local_rank])
+                file_s = (time.perf_counter() - t0) / file_steps
+                md5 = zf.Md5()
+                t0 = time.perf_counter()
+                md5.update(h_pcm_np)
+                digest = md5.final()
+                md5_s = time.perf_counter() - t0
+                e2e_file = {"value": round(nsamples * CHANNELS / file_s / 1e6, 2), "unit": UNIT, "ms_per_file": round(file_s * 1e3, 2),
+                            "md5_only_ms": round(md5_s * 1e3, 2), "flac_bytes": len(flac) if flac else None, "status": rc,
+                            "md5_matches_streaminfo": bool(flac and flac[26:42] == digest),
+                            "api": "zf_encode_wav_memory (reader | MD5 thread | encoder | writer pipeline over 2048-frame chunks)",
+                            "note": "warm library call; bounded by the serial MD5 of the PCM (md5_only_ms), which the reference computes too"}
+                # ... and the CLI as a user runs it: a fresh process (CUDA context creation included), files on tmpfs
+                cli = os.path.join(ROOT, "zig-flac_b200", "flac")
+                shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+                if os.path.exists(cli):
+                    import subprocess
+                    fin, fout = os.path.join(shm, f"zf_bench_{os.getpid()}.wav"), os.path.join(shm, f"zf_bench_{os.getpid()}.flac")
+                    try:
+                        wav.tofile(fin)
+                        t0 = time.perf_counter()
+                        r = subprocess.run([cli, fin, fout], capture_output=True, timeout=300)
+                        cli_s = time.perf_counter() - t0
+                        same_file = r.returncode == 0 and flac is not None and open(fout, "rb").read() == flac
+                        e2e_file["cli"] = {"wall_ms": round(cli_s * 1e3, 1), "exit": r.returncode, "same_bytes_as_library": bool(same_file),
+                                           "note": "`flac in.wav out.flac` in a fresh process: process start, CUDA context, file I/O on tmpfs included"}
+                    finally:
+                        for f in (fin, fout):
+                            if os.path.exists(f):
+                                os.remove(f)
+            del wav
+
+    except Exception as exc:  # the whole-file leg is an extra: never lose the bench line over it
+        e2e_file = {"error": repr(exc)}
 
     # the device-resident result and the host-path result are the same bytes
     same = bool((d_out[:flac_bytes].cpu().numpy() == got).all()) and flac_bytes == int(got.size)

@@ -18,4 +18,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:v3_kernel -c 1 -o gpurun_out/prof_${TAG}_c2 python bench.py --steps 1 --warmup 3 --profile > gpurun_out/${TAG}_ncu_c2.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:v3_kernel -c 1 -o gpurun_out/prof_${TAG}_c3 python bench.py --workload c3_32bit_192k_600s --steps 1 --warmup 3 --profile > gpurun_out/${TAG}_ncu_c3.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:v3_kernel -c 1 -o gpurun_out/prof_${TAG}_c1 python bench.py --workload c1_16bit_44k1_60s --steps 1 --warmup 3 --profile > gpurun_out/${TAG}_ncu_c1.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:zf_encode_stereo_kernel -c 1 -o gpurun_out/prof_${TAG}_tail python bench.py --workload c1_16bit_44k1_60s --steps 1 --warmup 3 --profile > gpurun_out/${TAG}_ncu_tail.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches_c1.csv python bench.py --workload c1_16bit_44k1_60s --steps 3 --warmup 3 --profile > gpurun_out/${TAG}_ncu_c1l.log 2>&1
+timeout 300 python bench.py --workload c4_16bit_44k1_60s_lpc12 --steps 30 --warmup 5 > gpurun_out/${TAG}_bench_c4.json 2>&1; tail -c 300 gpurun_out/${TAG}_bench_c4.json
 tail -2 gpurun_out/${TAG}_ncu_c3.log

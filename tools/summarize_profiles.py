@@ -8,7 +8,7 @@ kernel -- what bench.py reports as roofline.traffic / roofline.issue for that wo
 """
 import csv, json, os, shutil, subprocess, sys
 tag, out = sys.argv[1], sys.argv[2]
-for f in ['bench', 'bench_c1', 'bench_c3', 'bench_ref', 'bench_c5']:
+for f in ['bench', 'bench_c1', 'bench_c3', 'bench_c4', 'bench_ref', 'bench_c5']:
     src = f'gpurun_out/{tag}_{f}.json'
     if not os.path.exists(src):
         continue
