@@ -733,19 +733,23 @@ int zf_encode_pcm(zf_encoder *e, const uint8_t *pcm, uint64_t samples_per_channe
     if (out_len) *out_len = 0;
     if (frames > frame_sizes_cap && frame_sizes) return ZF_ERR_OUT_TOO_SMALL;
     const uint64_t per = e->cfg.max_frames_per_batch;
-    // Batch plan: full batches while more than one batch is left, then halves down to kMinTailBatch frames.  What follows
-    // the last upload -- that batch's kernels and its download -- is not overlapped with anything, so it is kept short.
+    // Batch plan: a ramp of growing batches (256, 512, ... frames), full batches while more than one batch is left, then
+    // halves down to kMinTailBatch frames.  The downloads are as long a chain as the uploads (both links run near 7 ms for
+    // the 10-minute stream when they share the bus), so the first download must not wait for a full batch to be uploaded
+    // and encoded; and what follows the last upload -- that batch's kernels and its download -- is overlapped with
+    // nothing, so it is kept short.
     std::vector<uint64_t> first;  // first frame of every batch, then the frame count
     {
         const uint64_t kMinTailBatch = 256;
         const bool taper = !e->no_taper;
-        uint64_t f = 0;
+        uint64_t f = 0, ramp = taper ? kMinTailBatch : per;
         while (f < frames) {
             const uint64_t left = frames - f;
-            uint64_t n = std::min(left, per);
-            if (taper && left <= per && left > 2 * kMinTailBatch) n = (left + 1) / 2;
+            uint64_t n = std::min(left, std::min(per, ramp));
+            if (taper && left <= per && left > 2 * kMinTailBatch && n > (left + 1) / 2) n = (left + 1) / 2;
             first.push_back(f);
             f += n;
+            ramp *= 2;
         }
         first.push_back(frames);
     }
