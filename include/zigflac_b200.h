@@ -67,6 +67,11 @@ typedef struct zf_config {
                                       Stereo with decorrelation, 8/16/24-bit only. */
     int32_t device_id;             /* CUDA device ordinal */
     uint32_t max_frames_per_batch; /* capacity of one submit; device buffers are sized from it */
+    uint8_t exact_rice;            /* 0 = the reference's Rice size estimate (rice.zig:402-405).  1 = extension: every partition's
+                                      parameter by its exact code length (what the reference's dead calcParamExact family,
+                                      rice.zig:110-245, set out to do) -- slightly smaller streams, no byte-parity claim.
+                                      Stereo with decorrelation, no LPC. */
+    uint8_t reserved1[3];
 } zf_config;
 
 typedef struct zf_encoder zf_encoder;

@@ -199,6 +199,7 @@ void zo_config_default(zo_config *cfg, uint8_t channels, uint8_t bit_depth) { /*
     cfg->max_rice_order = 8;
     cfg->max_rice_param = 30; /* rice.MAX_PARAM = MAX_PARAM_5BIT = 31 - 1, rice.zig:9-10 */
     cfg->lpc_order = 0;
+    cfg->exact_rice = 0;
 }
 
 size_t zo_max_frame_bytes(uint16_t block_size, uint8_t bit_depth, uint8_t channels, int stereo_decorrelation) {
@@ -429,6 +430,38 @@ static uint64_t rice_calc_optimal_params(unsigned part_order, uint16_t blk_size,
     return data_bits_size + (uint64_t)(config->method + 4) * part_count;
 }
 
+/* EXTENSION (zo_config.exact_rice; inert when 0): the parameter of every partition by its EXACT code length,
+ * sum (zigzag >> p) + n (p + 1), instead of the estimate of rice.zig:402-405 -- what the reference's dead
+ * calcParamExact family (rice.zig:110-245, never called, no escapes, SIMD-lane tables per target) set out to do.
+ * Same evaluation order and ties as the live search: escape first (5 + width n, valid up to width 31), then
+ * p = 0 .. max_param - 1 with strict '<'; method FIVE iff a chosen parameter exceeds 14; the caller keeps the
+ * highest partition order on ties.  maxs[] holds the partition widths (rice_calc_sums). */
+static uint64_t rice_exact_params(unsigned part_order, const int32_t *residuals, size_t len, unsigned max_param,
+                                  unsigned pred_order, const uint64_t *maxs, zo_rice_config *config) {
+    const size_t part_count = (size_t)1 << part_order;
+    const size_t part_size = len >> part_order;
+    config->method = 0;
+    config->part_order = (uint8_t)part_order;
+    uint64_t total = 0;
+    for (size_t p = 0; p < part_count; p++) {
+        const size_t start = p * part_size + (p == 0 ? pred_order : 0), end = (p + 1) * part_size;
+        const uint64_t n = end - start;
+        uint64_t best = (maxs[p] <= 31) ? 5 + maxs[p] * n : UINT64_MAX;
+        uint8_t choice = (uint8_t)((uint8_t)maxs[p] | 0x80);
+        for (unsigned param = 0; param < max_param; param++) {
+            uint64_t bits = n * (param + 1);
+            for (size_t i = start; i < end; i++) bits += calc_zigzag(residuals[i]) >> param;
+            if (bits < best) { best = bits; choice = (uint8_t)param; }
+        }
+        config->params[p] = choice;
+        total += best;
+    }
+    if (max_param > MAX_PARAM_4BIT)
+        for (size_t p = 0; p < part_count; p++)
+            if (!(config->params[p] & 0x80) && (config->params[p] & 0x7f) > MAX_PARAM_4BIT) config->method = 1;
+    return total + (uint64_t)(config->method + 4) * part_count;
+}
+
 /* rice.calcParams + calcParamEstimate, rice.zig:87-107,248-279 */
 static uint64_t rice_calc_params(zo_encoder *e, const int32_t *residuals, size_t len, unsigned max_part_order_cfg,
                                  unsigned max_param_cfg, unsigned bit_depth, unsigned pred_order,
@@ -453,8 +486,10 @@ static uint64_t rice_calc_params(zo_encoder *e, const int32_t *residuals, size_t
     for (unsigned po = 0; po <= mpo; po++) { /* :262-276 */
         zo_rice_config cfg;
         memset(&cfg, 0, sizeof cfg);
-        uint64_t bit_count = rice_calc_optimal_params(po, (uint16_t)len, maximum_param, pred_order,
-                                                      e->rice_sum_buf[po], e->rice_max_buf[po], &cfg);
+        uint64_t bit_count = e->config.exact_rice
+                                 ? rice_exact_params(po, residuals, len, maximum_param, pred_order, e->rice_max_buf[po], &cfg)
+                                 : rice_calc_optimal_params(po, (uint16_t)len, maximum_param, pred_order,
+                                                            e->rice_sum_buf[po], e->rice_max_buf[po], &cfg);
         if (bit_count <= optimal_bit_count) { /* <= : the highest partition order wins ties (Q7) */
             optimal_bit_count = bit_count;
             *out = cfg;

@@ -35,6 +35,8 @@ typedef struct {
     uint8_t max_rice_order;
     uint8_t max_rice_param;
     uint8_t lpc_order; /* 0 = the reference's path (fixed predictors only); 1..32 = LPC extension, zigflac_lpc.h */
+    uint8_t exact_rice; /* 0 = the reference's estimate (rice.zig:402-405); 1 = extension: exact code lengths */
+    uint8_t reserved;
 } zo_config;
 
 /* FrameInfo, encoder.zig:658-663 */

@@ -113,6 +113,7 @@ static int g_bytes, g_full, g_indep, g_v3;
 static int g_allow_v3 = 1;
 static unsigned g_bit_depth = 0;  // 0 = 8 x container bytes
 static unsigned g_lpc_order = 0;
+static unsigned g_exact = 0;
 static std::vector<uint16_t> g_win;
 static void make_window(uint32_t n) {  // zf-LPC v1 window, as zf_capi.cu computes it
     g_win.assign(n, 16384);
@@ -129,6 +130,12 @@ static void kernel_entry(void *) {
     if (g_lpc_order && !g_indep) {
         if (g_bytes == 2) zf::lpc::zf_encode_stereo_lpc_kernel<2>(g_job);
         else zf::lpc::zf_encode_stereo_lpc_kernel<3>(g_job);
+        return;
+    }
+    if (g_exact && !g_indep) {
+        if (g_bytes == 2) zf::zf_encode_stereo_kernel<2, false, true>(g_job);
+        else if (g_bytes == 3) zf::zf_encode_stereo_kernel<3, false, true>(g_job);
+        else zf::zf_encode_stereo_kernel<4, false, true>(g_job);
         return;
     }
     if (g_indep) {
@@ -189,7 +196,7 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     g_bytes = bytes_per_sample;
     if (full) {
         j.pcm = pcm; j.n_frames = (uint32_t)full; j.frame_base = 0; j.block_size = block_size;
-        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8 && g_bit_depth == 0 && !g_lpc_order;
+        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8 && g_bit_depth == 0 && !g_lpc_order && !g_exact;
         if (g_lpc_order) { make_window(block_size); j.lpc_window = g_win.data(); }
         g_v3 = g_full && g_allow_v3 && g_bit_depth == 0;
         g_job = j;
@@ -216,6 +223,7 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
 void emu_allow_v3(int on) { g_allow_v3 = on; }
 void emu_set_bit_depth(unsigned d) { g_bit_depth = d; }
 void emu_set_lpc_order(unsigned o) { g_lpc_order = o; }
+void emu_set_exact_rice(unsigned on) { g_exact = on; }
 unsigned long long emu_v3_frames(void) { return g_v3_frames; }
 unsigned long long emu_v3_wide_frames(void) { return zf::v3::g_emu_wide_frames; }
 unsigned long long emu_v3_narrow_frames(void) { return zf::v3::g_emu_narrow_frames; }

@@ -17,7 +17,8 @@ ORACLE_SO = os.path.join(ORACLE_DIR, "_ref", "libzigflac_oracle.so")
 class ZoConfig(C.Structure):
     _fields_ = [("block_size", C.c_uint16), ("bit_depth", C.c_uint8), ("channels", C.c_uint8),
                 ("stereo_decorrelation", C.c_uint8), ("max_rice_order", C.c_uint8),
-                ("max_rice_param", C.c_uint8), ("lpc_order", C.c_uint8)]
+                ("max_rice_param", C.c_uint8), ("lpc_order", C.c_uint8), ("exact_rice", C.c_uint8),
+                ("reserved", C.c_uint8)]
 
 
 class ZoFrameInfo(C.Structure):
@@ -148,7 +149,7 @@ def _buf(b):
 
 
 def config(channels=2, bit_depth=16, block_size=4096, stereo_decorrelation=1, max_rice_order=8, max_rice_param=30,
-           lpc_order=0):
+           lpc_order=0, exact_rice=0):
     cfg = ZoConfig()
     lib().zo_config_default(C.byref(cfg), channels, bit_depth)
     cfg.block_size = block_size
@@ -156,6 +157,7 @@ def config(channels=2, bit_depth=16, block_size=4096, stereo_decorrelation=1, ma
     cfg.max_rice_order = max_rice_order
     cfg.max_rice_param = max_rice_param
     cfg.lpc_order = lpc_order  # 0 = the reference's path; > 0 = LPC extension (oracle/zigflac_lpc.h)
+    cfg.exact_rice = exact_rice  # 0 = the reference's estimate; 1 = extension: exact Rice code lengths
     return cfg
 
 

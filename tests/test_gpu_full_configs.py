@@ -276,3 +276,31 @@ def test_lpc_input_classes(zf, oracle):
                 assert ref.tobytes() == got.tobytes(), (name, bits)
                 d = oracle.decode(oracle.wrap_frames(got, 2, bits, 48000))
                 assert d["rc"] == 0 and np.array_equal(d["pcm"], signals.interleave([L, R])), (name, bits)
+
+
+@pytest.mark.parametrize("bits,rate", [(16, 44100), (24, 96000), (32, 192000)])
+def test_exact_rice_extension(zf, oracle, bits, rate):
+    """zf_config.exact_rice (extension; upstream only has dead code for it, rice.zig:110-245): GPU == the oracle's
+    brute-force statement of the rule, lossless, never larger than the estimate's stream."""
+    import signals
+    n = 40 * BLOCK + 1234
+    pcm = zf.synth_pcm(n, rate, bits)
+    with zf.Encoder(zf.Config(2, bits, exact_rice=True), rate, max_frames_per_batch=16) as enc:
+        got, sizes = enc.encode_pcm(pcm, n, 9)
+        ref, ref_sizes = oracle.encode_pcm(pcm, n, oracle.config(2, bits, exact_rice=1), rate, 9, threads=os.cpu_count() or 1)
+        _compare_stream(got, sizes, ref, ref_sizes, f"exact rice {bits}-bit")
+        est, _ = oracle.encode_pcm(pcm, n, oracle.config(2, bits), rate, 9, threads=os.cpu_count() or 1)
+        assert got.size <= est.size
+        d = oracle.decode(oracle.wrap_frames(got, 2, bits, rate, total_samples=n), max_frames=1 << 12)
+        assert d["rc"] == 0 and d["n_frames"] == sizes.size
+        for name, L, R in signals.stereo_classes(bits):
+            p = oracle.pcm_bytes_from_int(signals.interleave([L, R]), bits)
+            r, rs = oracle.encode_pcm(p, L.size, oracle.config(2, bits, exact_rice=1), rate, 0)
+            g, gs = enc.encode_pcm(p, L.size, 0)
+            assert np.array_equal(rs, gs) and r.tobytes() == g.tobytes(), (name, bits)
+    for bad in (dict(channels=1), dict(lpc_order=8), dict(stereo_decorrelation=False)):
+        kw = dict(channels=2, exact_rice=True)
+        kw.update(bad)
+        ch = kw.pop("channels")
+        with pytest.raises(zf.FlacGpuError):
+            zf.Encoder(zf.Config(ch, 16 if bits == 32 else bits, **kw), rate)

@@ -310,3 +310,37 @@ def test_random_configurations_emulated(emu, oracle):
         planes = [np.clip((rng.normal(0, F * 10.0 ** rng.uniform(-4, -0.5), n)).astype(np.int64), -F, F - 1) for _ in range(channels)]
         pcm = oracle.pcm_bytes_from_int(signals.interleave(planes), bits)
         _check(emu, oracle, pcm, n, bits, channels=channels, block=block, mro=mro, mrp=mrp, rate=48000)
+
+
+@pytest.mark.parametrize("bits", [16, 24, 32])
+def test_exact_rice_search_kernel_logic(emu, oracle, bits):
+    """Extension (zf_config.exact_rice): Rice parameters by exact code length -- per-partition bit counters, additive over
+    the partition tree, E_p = cnt_p + 2 E_{p+1} -- against the oracle's brute-force statement of the same rule; streams
+    decode losslessly and are never larger than the estimate's."""
+    import zigflac_b200 as zf
+    emu.emu_set_exact_rice.argtypes = [C.c_uint]
+    rng = np.random.default_rng(100 + bits)
+    F = 1 << (bits - 1)
+    cases = [("synthetic", zf.synth_pcm(4096 + 1500, 96000, bits), 4096 + 1500, {})]
+    for name, a, b in signals.stereo_classes(bits, n=4096 + 700):
+        cases.append((name, oracle.pcm_bytes_from_int(signals.interleave([a, b]), bits), a.size, {}))
+    for block, mro, mrp in ((576, 8, 30), (1000, 3, 14), (4080, 8, 30), (2048, 8, 5), (16, 8, 30), (4096, 6, 30)):
+        n = block + block // 3 + 1
+        x = (0.2 * F * np.sin(np.arange(n) * 0.05)).astype(np.int64) + rng.integers(-F // 1000 - 2, F // 1000 + 3, n)
+        cases.append((f"block{block}", oracle.pcm_bytes_from_int(signals.interleave([x, x // 2 + rng.integers(-3, 4, n)]), bits), n,
+                      dict(block=block, mro=mro, mrp=mrp)))
+    try:
+        emu.emu_set_exact_rice(1)
+        for name, pcm, n, kw in cases:
+            cfg = oracle.config(2, bits, block_size=kw.get("block", 4096), max_rice_order=kw.get("mro", 8),
+                                max_rice_param=kw.get("mrp", 30), exact_rice=1)
+            ref, rs = oracle.encode_pcm(pcm, n, cfg, 48000, 0)
+            got, gs = _emu_encode(emu, pcm, n, bits, rate=48000, **kw)
+            assert np.array_equal(rs, gs), name
+            assert ref.tobytes() == got.tobytes(), name
+            assert oracle.decode(oracle.wrap_frames(got, 2, bits, 48000, block_size=kw.get("block", 4096)))["rc"] == 0, name
+            cfg.exact_rice = 0
+            est, _ = oracle.encode_pcm(pcm, n, cfg, 48000, 0)
+            assert got.size <= est.size, name
+    finally:
+        emu.emu_set_exact_rice(0)

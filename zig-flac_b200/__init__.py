@@ -42,7 +42,8 @@ class ZfConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("block_size", C.c_uint16), ("bit_depth", C.c_uint8),
                 ("channels", C.c_uint8), ("sample_rate", C.c_uint32), ("stereo_decorrelation", C.c_uint8),
                 ("max_rice_order", C.c_uint8), ("max_rice_param", C.c_uint8), ("lpc_order", C.c_uint8),
-                ("device_id", C.c_int32), ("max_frames_per_batch", C.c_uint32)]
+                ("device_id", C.c_int32), ("max_frames_per_batch", C.c_uint32), ("exact_rice", C.c_uint8),
+                ("reserved1", C.c_uint8 * 3)]
 
 
 class ZfStreamInfo(C.Structure):
@@ -154,7 +155,7 @@ class Config:
     """Encoder.Config (encoder.zig:609-656); `default` is Config.default(channels, bit_depth) (:642-655)."""
 
     def __init__(self, channels, bit_depth, block_size=4096, stereo_decorrelation=True, max_rice_order=8,
-                 max_rice_param=30, lpc_order=0):
+                 max_rice_param=30, lpc_order=0, exact_rice=False):
         self.channels = channels
         self.bit_depth = bit_depth
         self.block_size = block_size
@@ -162,6 +163,7 @@ class Config:
         self.max_rice_order = max_rice_order
         self.max_rice_param = max_rice_param
         self.lpc_order = lpc_order  # 0 = the reference's encoder; 1..12 = LPC extension (no reference counterpart)
+        self.exact_rice = exact_rice  # extension: exact Rice code lengths instead of the reference's estimate
 
     @staticmethod
     def default(channels, bit_depth):
@@ -175,6 +177,7 @@ class Config:
         c.max_rice_order = self.max_rice_order
         c.max_rice_param = self.max_rice_param
         c.lpc_order = self.lpc_order
+        c.exact_rice = 1 if self.exact_rice else 0
         c.device_id = device_id
         c.max_frames_per_batch = max_frames_per_batch
         return c

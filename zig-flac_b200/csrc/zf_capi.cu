@@ -88,8 +88,8 @@ struct zf_encoder {
     size_t frame_dev_bytes = 0;   // ... and as the kernels read it (differs for 8-bit samples)
     size_t max_frame_bytes = 0;
     bool stereo = false;
-    int occ_gen = 0, occ_v3 = 0, occ_lpc = 0;
-    size_t smem_lpc = 0;
+    int occ_gen = 0, occ_v3 = 0, occ_lpc = 0, occ_exact = 0;
+    size_t smem_lpc = 0, smem_exact = 0;
     uint16_t *d_win = nullptr;  // LPC: window of a full block
     size_t smem_stereo = 0;
     size_t smem_v3 = 0;
@@ -137,6 +137,16 @@ int setup_stereo_kernel(zf_encoder *e, int *occ) {
     ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ZF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, zf::kThreads, smem));
     e->smem_stereo = smem;
+    return ZF_OK;
+}
+
+template <int BYTES>
+int setup_exact_kernel(zf_encoder *e, int *occ) {
+    void (*k)(const zf::FrameJob) = zf::zf_encode_stereo_kernel<BYTES, false, true>;
+    const size_t smem = sizeof(zf::SmemStereoExact<BYTES>);
+    ZF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, zf::kThreads, smem));
+    e->smem_exact = smem;
     return ZF_OK;
 }
 
@@ -193,6 +203,15 @@ int setup_kernels(zf_encoder *e) {
         else if (bytes == 3) rc = setup_indep_kernel<3>(e, &e->occ_gen);
         else rc = setup_indep_kernel<4>(e, &e->occ_gen);
     }
+    if (!rc && e->cfg.exact_rice) {
+        if (bytes == 2) rc = setup_exact_kernel<2>(e, &e->occ_exact);
+        else if (bytes == 3) rc = setup_exact_kernel<3>(e, &e->occ_exact);
+        else rc = setup_exact_kernel<4>(e, &e->occ_exact);
+        if (!rc && e->occ_exact < 1) {
+            snprintf(g_cuda_err, sizeof g_cuda_err, "exact-search kernel does not fit on an SM");
+            rc = ZF_ERR_CUDA;
+        }
+    }
     if (!rc && e->cfg.lpc_order) {
         if (bytes == 2) rc = setup_lpc_kernel<2>(e, &e->occ_lpc);
         else rc = setup_lpc_kernel<3>(e, &e->occ_lpc);
@@ -237,6 +256,12 @@ void launch_one(zf_encoder *e, int grid, cudaStream_t s, const zf::FrameJob &job
     if (e->cfg.lpc_order) {
         if (bytes == 2) launch_k(zf::lpc::zf_encode_stereo_lpc_kernel<2>, grid, zf::kThreads, e->smem_lpc, s, overlap, job);
         else launch_k(zf::lpc::zf_encode_stereo_lpc_kernel<3>, grid, zf::kThreads, e->smem_lpc, s, overlap, job);
+        return;
+    }
+    if (e->cfg.exact_rice) {
+        if (bytes == 2) launch_k(zf::zf_encode_stereo_kernel<2, false, true>, grid, zf::kThreads, e->smem_exact, s, overlap, job);
+        else if (bytes == 3) launch_k(zf::zf_encode_stereo_kernel<3, false, true>, grid, zf::kThreads, e->smem_exact, s, overlap, job);
+        else launch_k(zf::zf_encode_stereo_kernel<4, false, true>, grid, zf::kThreads, e->smem_exact, s, overlap, job);
         return;
     }
     if (e->stereo) {
@@ -295,7 +320,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
     }
     // the fast kernel covers the reference's default shape: 4096-sample frames, max_rice_order 8, 16/24/32-bit samples
     const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.max_rice_order == 8 && e->cfg.bit_depth != 8 &&
-                      !e->cfg.lpc_order;
+                      !e->cfg.lpc_order && !e->cfg.exact_rice;
     if (e->cfg.lpc_order && tail && sl.win_tail_len != tail) {  // the short last frame has a window of its own length
         std::vector<uint16_t> w;
         lpc_window(tail, w);
@@ -343,7 +368,7 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         if (split_tail) job.batch_frames = (uint32_t)full;  // the full-frame kernel closes its own total
         // full 4096-sample stereo frames with the reference's partition depth: the lean 256-thread kernel (zf_kernel_v3.cuh)
         const bool v3 = fast && e->occ_v3 > 0;
-        const int occ = e->cfg.lpc_order ? e->occ_lpc : v3 ? e->occ_v3 : e->occ_gen;
+        const int occ = e->cfg.lpc_order ? e->occ_lpc : e->cfg.exact_rice ? e->occ_exact : v3 ? e->occ_v3 : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
         if (v3) {
             if (e->cfg.bit_depth == 16) launch_k(zf::v3::zf_encode_stereo_v3_kernel<2>, grid, zf::v3::kT, e->smem_v3, s, split_tail, job);
@@ -611,6 +636,9 @@ int zf_encoder_create(const zf_config *cfg, zf_encoder **out) {
     if (cfg->max_rice_order > 8) return ZF_ERR_UNSUPPORTED;            // rice.MAX_ORDER = 8 (rice.zig:12)
     if (cfg->max_rice_param == 0 || cfg->max_rice_param > 30) return ZF_ERR_UNSUPPORTED;  // 0: overflow upstream
     if (cfg->max_frames_per_batch == 0) return ZF_ERR_INVALID_ARG;
+    if (cfg->exact_rice) {  // the exact-search extension: the general stereo kernel only
+        if (cfg->exact_rice > 1 || cfg->lpc_order || cfg->channels != 2 || !cfg->stereo_decorrelation) return ZF_ERR_UNSUPPORTED;
+    }
     if (cfg->lpc_order) {  // the LPC extension (no reference counterpart): stereo with decorrelation, 8/16/24-bit, order <= 12
         if (cfg->lpc_order > zf::lpc::kMaxOrder || cfg->channels != 2 || !cfg->stereo_decorrelation || cfg->bit_depth == 32)
             return ZF_ERR_UNSUPPORTED;

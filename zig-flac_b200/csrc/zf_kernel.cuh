@@ -1012,6 +1012,140 @@ ZF_DEVICE void rice_tree_and_search(SmemCommon &c, int t, uint32_t n, uint32_t n
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------------
+// EXTENSION (zf_config.exact_rice): the Rice parameter of every partition by its exact code length
+// sum (zigzag >> p) + n (p + 1) instead of the estimate of rice.zig:402-405.  The reference only has dead code for this
+// (calcParamExact, rice.zig:110-245: never called, no escapes), so the rule is ours: same evaluation order and ties
+// as the live search (escape first, then p = 0 .. P-1 with strict '<').
+//
+// sum_j (zz_j >> p) = sum_{b >= p} cnt_b 2^(b-p) with cnt_b = how many zigzags have bit b set, so 32 counters per
+// partition -- additive over the partition tree -- give the exact length for every p by E_p = cnt_p + 2 E_{p+1}.
+// They are kept as sixteen words of two 16-bit counters (bit i low, bit i + 16 high; a frame has at most 4096 samples).
+// One candidate at a time through `cnt` (heap numbering as psum / pbits).
+// ---------------------------------------------------------------------------------------------------
+ZF_DEVICE void rice_exact_slot(SmemCommon &c, uint32_t (*cnt)[16], uint32_t s, const int32_t (&r)[kSpt], int t, uint32_t base,
+                               uint32_t n) {
+    const int lane = t & 31;
+    const SlotDec d = c.dec[s];
+    const uint32_t order = d.order, mpo = d.mpo;
+    const uint32_t psz = n >> mpo;
+    const uint32_t leaf0 = (1u << mpo) - 1u;
+    for (uint32_t idx = t; idx < (16u << mpo); idx += kThreads) cnt[leaf0 + (idx >> 4)][idx & 15u] = 0;
+    if (t <= kMaxLevel) c.levelcost[s][t] = 0;
+    if (t == 0) c.levelfive[s] = 0;
+    __syncthreads();
+    {   // leaves: a thread's samples fall into runs of one partition each
+        uint32_t zz[kSpt], part[kSpt];
+        const uint32_t p0 = base < n ? base / psz : 0u;
+        uint32_t pp = p0, next = (p0 + 1u) * psz;
+#pragma unroll
+        for (int j = 0; j < kSpt; j++) {
+            const uint32_t i = base + j;
+            if (i < n && i >= next) { pp++; next += psz; }
+            const bool v = i < n && i >= order;
+            zz[j] = v ? zigzag(r[j]) : 0u;
+            part[j] = pp;
+        }
+        // whole warp inside one partition (the usual case for the coarse geometries of short frames): one REDUX per word
+        const uint32_t il = (base + kSpt <= n) ? base + kSpt - 1u : n - 1u;  // this thread's last sample
+        const bool one = il < (p0 + 1u) * psz;
+        const uint32_t lead = __shfl_sync(0xffffffffu, p0, 0);
+        const uint32_t live = __ballot_sync(0xffffffffu, base < n);
+        const bool uniform = live != 0u && __ballot_sync(0xffffffffu, base < n && one && p0 == lead) == live;
+#pragma unroll 1
+        for (uint32_t w = 0; w < 16; w++) {
+            if (uniform) {
+                uint32_t a = 0;
+#pragma unroll
+                for (int j = 0; j < kSpt; j++) a += (zz[j] >> w) & 0x00010001u;
+                a = reduce_add(base < n ? a : 0u);  // at most 32 x 8 per half: no carry between the halves
+                if (lane == 0 && a) atomicAdd(&cnt[leaf0 + lead][w], a);
+            } else {
+                uint32_t a = 0, cur = p0;
+#pragma unroll
+                for (int j = 0; j < kSpt; j++) {
+                    if (part[j] != cur) {
+                        if (a) atomicAdd(&cnt[leaf0 + cur][w], a);
+                        a = 0;
+                        cur = part[j];
+                    }
+                    a += (zz[j] >> w) & 0x00010001u;
+                }
+                if (a) atomicAdd(&cnt[leaf0 + cur][w], a);
+            }
+        }
+    }
+    __syncthreads();
+    for (uint32_t step = 1; step <= mpo; step++) {  // partition tree: counters add
+        const uint32_t lvl = mpo - step;
+        const uint32_t b0 = (1u << lvl) - 1u, b1 = (2u << lvl) - 1u;
+        for (uint32_t idx = t; idx < (16u << lvl); idx += kThreads) {
+            const uint32_t j = idx >> 4, w = idx & 15u;
+            cnt[b0 + j][w] = cnt[b1 + 2 * j][w] + cnt[b1 + 2 * j + 1][w];
+        }
+        __syncthreads();
+    }
+    const uint32_t last = (2u << mpo) - 1u;
+    for (uint32_t m0 = 0; m0 <= last; m0 += kThreads) {
+        const uint32_t m = m0 + t;
+        const bool act = m >= 1 && m <= last;
+        uint32_t lvl = 0, choice = 0;
+        unsigned long long cost = 0;
+        if (act) {
+            lvl = floor_log2(m);
+            const uint32_t j = m - (1u << lvl);
+            const uint32_t ne = (n >> lvl) - (j == 0 ? order : 0u);  // rice.zig:356,371
+            uint32_t cb[32];
+#pragma unroll
+            for (int w = 0; w < 16; w++) {
+                const uint32_t v = cnt[m - 1][w];
+                cb[w] = v & 0xffffu;
+                cb[w + 16] = v >> 16;
+            }
+            uint32_t B = 0;
+#pragma unroll
+            for (int b = 0; b < 32; b++)
+                if (cb[b]) B = (uint32_t)b + 1u;
+            unsigned long long E = 0, bestc = kU64Max;
+            uint32_t bestp = 0;
+#pragma unroll
+            for (int b = 31; b >= 0; b--) {  // downwards with '<=': the lowest parameter wins ties, as the upward '<' scan does
+                E = (unsigned long long)cb[b] + 2ull * E;
+                if ((uint32_t)b < d.max_param) {
+                    const unsigned long long cc = E + (unsigned long long)ne * ((uint32_t)b + 1u);
+                    if (cc <= bestc) { bestc = cc; bestp = (uint32_t)b; }
+                }
+            }
+            const unsigned long long esc = (B <= 31u) ? 5ull + (unsigned long long)B * ne : kU64Max;
+            if (bestc < esc) { cost = bestc; choice = bestp; }  // the escape wins ties (it is evaluated first upstream)
+            else { cost = esc; choice = 0x80u | B; }
+            c.pchoice[s][m - 1] = (uint8_t)choice;
+        }
+        const bool five = act && choice < 0x80u && choice > 14u;
+        if (m0 == 0 && t < 32) {
+#pragma unroll 1
+            for (uint32_t q = 0; q < 5; q++) {
+                const unsigned long long ws = warp_sum((act && lvl == q) ? cost : 0ull);
+                const uint32_t wf = reduce_or((five && lvl == q) ? 1u : 0u);
+                if (lane == 0 && q <= mpo) {
+                    c.levelcost[s][q] += ws;
+                    if (wf) atomicOr(&c.levelfive[s], 1u << q);
+                }
+            }
+        } else {
+            const unsigned long long wsum = warp_sum(cost);
+            const uint32_t wfive = reduce_or(five ? 1u : 0u);
+            const uint32_t wl = __shfl_sync(0xffffffffu, lvl, 0);
+            const uint32_t wact = __shfl_sync(0xffffffffu, act ? 1u : 0u, 0);
+            if (lane == 0 && wact) {
+                atomicAdd(&c.levelcost[s][wl], wsum);
+                if (wfive) atomicOr(&c.levelfive[s], 1u << wl);
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // pick the partition order (rice.zig:262-276: '<=' keeps the highest on ties) and FIXED vs VERBATIM (:538)
 ZF_DEVICE void finish_slot(SmemCommon &c, uint32_t s, uint32_t n) {
     SlotDec &d = c.dec[s];
@@ -1148,8 +1282,15 @@ ZF_DEVICE void load_raw_generic(uint32_t *raw, const uint8_t *src, uint32_t nbyt
     }
 }
 
-template <int BYTES, bool FULL>
-__global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_kernel(const FrameJob job) {
+// with the exact Rice search (extension): the partition tree's bit counters behind the ordinary layout
+template <int BYTES>
+struct SmemStereoExact {
+    SmemStereo<BYTES> base;
+    alignas(16) uint32_t cnt[kNodes][16];
+};
+
+template <int BYTES, bool FULL, bool EXACT = false>
+__global__ void __launch_bounds__(kThreads, EXACT ? 1 : 2) zf_encode_stereo_kernel(const FrameJob job) {
     constexpr bool WIDE = (BYTES == 4);
     typedef typename Ar<WIDE>::T T;
     extern __shared__ __align__(16) unsigned char zf_smem[];
@@ -1240,6 +1381,18 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_kernel(const Fra
         __syncthreads();
 
         // ---- pass 2: Rice analysis of the tentative FIXED candidates ----
+        if constexpr (EXACT) {
+            uint32_t (*cnt)[16] = reinterpret_cast<SmemStereoExact<BYTES> *>(zf_smem)->cnt;
+#pragma unroll 1
+            for (uint32_t s = 0; s < 4; s++) {
+                if (c.dec[s].kind != kFixed) continue;  // block-uniform
+                make_x<WIDE>(s, L, R, x);
+                int32_t r[kSpt];
+#pragma unroll
+                for (int j = 0; j < kSpt; j++) r[j] = (int32_t)(fixed_residual<T>(x, c.dec[s].order, j) >> c.dec[s].waste);
+                rice_exact_slot(c, cnt, s, r, t, base, n);
+            }
+        } else {
         if (!FULL || job.max_rice_order != (uint32_t)kMaxLevel) {
             for (uint32_t s = 0; s < 4; s++) rice_zero_leaves(c, s, t, n);
             __syncthreads();
@@ -1252,6 +1405,7 @@ __global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_kernel(const Fra
         }
         __syncthreads();
         rice_tree_and_search(c, t, n, 4);
+        }
         if (t == 0) {
             for (uint32_t s = 0; s < 4; s++) finish_slot(c, s, n);
             // stereo mode: first minimum of [L+R, L+S, S+R, M+S], encoder.zig:441-452
