@@ -369,6 +369,11 @@ int zf_encode_wav_memory(const uint8_t *wav, size_t wav_len, uint8_t **flac, siz
     src.mem = wav + fmt.data_offset;
     src.mem_left = wav_len - (size_t)fmt.data_offset;
     Sink sink;
+    // room for the usual outcome up front (lossless audio seldom falls below half or rises above the input): growing the
+    // buffer by doubling copies the stream a second time
+    sink.cap = kPrefix + (src.mem_left / 4) * 3 + (1u << 20);
+    sink.buf = (uint8_t *)malloc(sink.cap);
+    if (!sink.buf) return ZF_ERR_NOMEM;
     rc = encode_stream(src, sink, fmt, fmt.samples_count, devices, n_devices);
     if (rc) { free(sink.buf); return rc; }
     *flac = sink.buf;
