@@ -196,9 +196,9 @@ long long emu_encode(const uint8_t *pcm, unsigned long long samples, int bytes_p
     g_bytes = bytes_per_sample;
     if (full) {
         j.pcm = pcm; j.n_frames = (uint32_t)full; j.frame_base = 0; j.block_size = block_size;
-        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && max_rice_order == 8 && g_bit_depth == 0 && !g_lpc_order && !g_exact;
+        g_full = (block_size == (unsigned)zf::kMaxBlock) && !g_indep && g_bit_depth == 0 && !g_lpc_order && !g_exact;
         if (g_lpc_order) { make_window(block_size); j.lpc_window = g_win.data(); }
-        g_v3 = g_full && g_allow_v3 && g_bit_depth == 0;
+        g_v3 = g_full && g_allow_v3 && g_bit_depth == 0 && (bytes_per_sample != 4 || max_rice_param >= 20);
         g_job = j;
         ticket = 0;
         if (g_v3) g_v3_frames += full;

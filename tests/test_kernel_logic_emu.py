@@ -289,10 +289,12 @@ def test_v3_kernel_any_rice_limit_and_sample_rate(emu, oracle, bits):
     before = emu.emu_v3_frames()
     for mrp in (1, 2, 5, 14, 15, 29, 30):
         _check(emu, oracle, pcm, n, bits, rate=96000, mrp=mrp)
+    for mro in (0, 1, 3, 5, 7):
+        _check(emu, oracle, pcm, n, bits, rate=96000, mro=mro)
     for rate in (200, 255, 256, 11025, 12345, 65535, 65536, 100000, 1048575):
         _check(emu, oracle, pcm, n, bits, rate=rate, first=(1 << 21) + 3)
         _check(emu, oracle, pcm, n, bits, rate=rate, first=5)
-    assert emu.emu_v3_frames() - before == 2 * (7 + 18)
+    assert emu.emu_v3_frames() - before == 2 * ((7 if bits < 32 else 2) + 5 + 18)  # 32-bit with a low parameter limit: general kernel
 
 
 def test_random_configurations_emulated(emu, oracle):

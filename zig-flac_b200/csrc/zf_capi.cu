@@ -318,8 +318,8 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         d_pcm = sl.d_wide;
         (*launches)++;
     }
-    // the fast kernel covers the reference's default shape: 4096-sample frames, max_rice_order 8, 16/24/32-bit samples
-    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.max_rice_order == 8 && e->cfg.bit_depth != 8 &&
+    // the fast kernel covers the reference's default block: 4096-sample frames of 16/24/32-bit samples, any Rice limits
+    const bool fast = e->stereo && bs == (uint32_t)zf::kMaxBlock && e->cfg.bit_depth != 8 &&
                       !e->cfg.lpc_order && !e->cfg.exact_rice;
     if (e->cfg.lpc_order && tail && sl.win_tail_len != tail) {  // the short last frame has a window of its own length
         std::vector<uint16_t> w;
@@ -367,7 +367,9 @@ int launch_batch(zf_encoder *e, Slot &sl, const uint8_t *d_pcm, uint64_t samples
         job.ticket = sl.d_ctl + 0;
         if (split_tail) job.batch_frames = (uint32_t)full;  // the full-frame kernel closes its own total
         // full 4096-sample stereo frames with the reference's partition depth: the lean 256-thread kernel (zf_kernel_v3.cuh)
-        const bool v3 = fast && e->occ_v3 > 0;
+        // (32-bit PCM with a low max_rice_param stays with the general kernel: where no escape is possible -- residuals of
+        // 32 bits -- and no high parameter either, partition costs exceed the lean kernel's 32-bit cost arithmetic)
+        const bool v3 = fast && e->occ_v3 > 0 && (e->cfg.bit_depth != 32 || e->cfg.max_rice_param >= 20);
         const int occ = e->cfg.lpc_order ? e->occ_lpc : e->cfg.exact_rice ? e->occ_exact : v3 ? e->occ_v3 : e->occ_gen;
         const int grid = (int)std::min<uint64_t>(full, (uint64_t)e->sm_count * occ);
         if (v3) {

@@ -1,5 +1,5 @@
-// zf_kernel_v3.cuh -- lean full-frame stereo kernel for 16- and 24-bit PCM (block 4096, max_rice_order 8,
-// max_rice_param 30, a sample rate with a header code of its own).  Same decisions and the same bytes as
+// zf_kernel_v3.cuh -- lean full-frame stereo kernel for 16-, 24- and 32-bit PCM (block 4096; any max_rice_order, max_rice_param
+// and sample rate).  Same decisions and the same bytes as
 // zf_kernel.cuh / the oracle, arranged around the B200's issue limits (the path is integer-issue bound, not HBM
 // bound -- DESIGN.md section 4):
 //
@@ -1470,6 +1470,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                     const uint32_t method = (fv.x | fv.y | fv.z | fv.w) ? 1u : 0u;
                     const uint32_t bc = cost + ((4u + method) << l);  // :394
                     key = (bc << 5) | ((15u - l) << 1) | method;
+                    if (l > job.max_rice_order) key = 0xffffffffu;  // rice.calcParams: orders above Config.max_rice_order are not tried
                     if (l == 1u) {
                         const uint32_t m0 = sm.lvlfive[s][0][0] ? 1u : 0u;
                         const uint32_t k0 = ((sm.lvlcost[s][0][0] + 4u + m0) << 5) | (15u << 1) | m0;
