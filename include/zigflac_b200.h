@@ -45,7 +45,12 @@ enum {
     ZF_ERR_WAV_BIT_DEPTH = -21,/* EncodingError.UnsupportBitDepth wav_reader.zig:263 */
     ZF_ERR_WAV_NO_DATA = -22,  /* EncodingError.DataNotFound    wav_reader.zig:265 */
     ZF_ERR_WAV_BIT_RATE = -23, /* EncodingError.BitRateUnmatch  wav_reader.zig:267 */
-    ZF_ERR_WAV_INCOMPLETE = -24/* StreamError.IncompleteStream  wav_reader.zig:273 */
+    ZF_ERR_WAV_INCOMPLETE = -24,/* StreamError.IncompleteStream  wav_reader.zig:273 */
+    ZF_ERR_FLAC_NOT_FLAC = -32, /* decoder: no "fLaC" marker / no STREAMINFO block */
+    ZF_ERR_FLAC_TRUNCATED = -33,/* decoder: metadata or the first frame runs past the end of the stream */
+    ZF_ERR_FLAC_FRAME = -34,    /* decoder: a frame failed (zf_decode_info.bad_frame / bad_frame_status say which and why) */
+    ZF_ERR_FLAC_COUNT = -35,    /* decoder: decoded sample count differs from STREAMINFO's */
+    ZF_ERR_FLAC_MD5 = -36       /* decoder: ZF_DECODE_REQUIRE_MD5 and the MD5 of the decoded samples differs */
 };
 
 /* Encoder.Config + Config.Feature (encoder.zig:609-656) plus what FrameInfo (encoder.zig:658-663)
@@ -233,6 +238,56 @@ void zf_driver_release_cache(void);
  */
 int zf_host_alloc(size_t bytes, void **out);
 void zf_host_free(void *p);
+
+/* ---- decoder (extension: SURVEY.md 8(f) rank 4) ------------------------------------------------------------
+ *
+ * The reference has no decoder (readme.md:33 lists it as queued work), so these entries replace nothing upstream; the
+ * contract is the FLAC format (RFC 9639).  Fixed-blocksize streams of 8/16/24/32-bit samples, 1..8 channels, every
+ * subframe type, i.e. everything the encode entries above (and libFLAC's default settings) produce.  All decoding runs
+ * on the device (zf_kernel_decode.cuh: header scan, one thread per frame for the serial bit parse, CRC-16, inter-channel
+ * restore and interleave); only the metadata blocks, the chaining of frame headers by frame number and the optional
+ * MD5 are host work.  No CPU fallback.
+ */
+typedef struct zf_decoder zf_decoder;
+
+#define ZF_DECODE_CHECK_MD5 1u    /* MD5 the decoded samples on the host and compare with STREAMINFO (md5_status) */
+#define ZF_DECODE_REQUIRE_MD5 2u  /* ... and fail with ZF_ERR_FLAC_MD5 when it differs (a zero STREAMINFO MD5 passes) */
+
+typedef struct zf_decode_info {
+    uint32_t struct_size;          /* set by the caller to sizeof(zf_decode_info) */
+    uint32_t sample_rate, channels, bit_depth, min_block_size, max_block_size;
+    uint32_t launches;             /* kernel launches of the call */
+    float kernel_ms;               /* device time of those kernels (CUDA events) */
+    uint64_t samples_per_channel;  /* decoded */
+    uint64_t streaminfo_samples;   /* STREAMINFO's total (0 = unknown) */
+    uint64_t pcm_bytes;            /* samples_per_channel * channels * bit_depth / 8 */
+    uint64_t n_frames;
+    uint64_t bad_frame;            /* ZF_ERR_FLAC_FRAME: index of the first failing frame ... */
+    uint32_t bad_frame_status;     /* ... and why: 1 header, 2 reserved value, 3 range, 4 overrun, 5 length, 6 padding, 7 CRC-16 */
+    int32_t md5_status;            /* 1 match, 0 mismatch, -1 not checked or STREAMINFO carries no MD5 */
+    uint8_t md5[16];               /* STREAMINFO's */
+} zf_decode_info;
+
+int zf_decoder_create(int device_id, zf_decoder **out);
+void zf_decoder_destroy(zf_decoder *dec);
+/* STREAMINFO of a stream in host memory (host only, no device needed). */
+int zf_flac_stream_info(const uint8_t *flac, size_t len, zf_decode_info *info);
+/*
+ * Decodes a whole FLAC stream from host memory into `pcm`: interleaved little-endian samples of bit_depth / 8 bytes,
+ * signed (8-bit too) -- the layout zf_encode_pcm takes.  Page-locked buffers (zf_host_alloc) are copied from / into
+ * directly.  ZF_ERR_OUT_TOO_SMALL when pcm_cap < info->pcm_bytes (info is filled in, so the call can be repeated).
+ */
+int zf_decode_flac(zf_decoder *dec, const uint8_t *flac, size_t len, uint8_t *pcm, size_t pcm_cap, size_t *pcm_len,
+                   uint32_t flags, zf_decode_info *info);
+/* The same with device pointers on the decoder's device (nothing but the frame table crosses PCIe); MD5 flags are
+ * not available here.  Blocking. */
+int zf_decode_flac_device(zf_decoder *dec, const void *d_flac, size_t len, void *d_pcm, size_t pcm_cap, size_t *pcm_len,
+                          zf_decode_info *info);
+/* Convenience: *pcm is malloc'd (zf_free). */
+int zf_decode_flac_memory(const uint8_t *flac, size_t len, int device_id, uint32_t flags, uint8_t **pcm, size_t *pcm_len,
+                          zf_decode_info *info);
+/* `flac -d in.flac out.wav`: canonical PCM WAV (8-bit samples become unsigned, as WAV stores them). */
+int zf_decode_flac_file(const char *in_path, const char *out_path, int device_id, uint32_t flags);
 
 /* ---- benchmark / test utility --------------------------------------------------------------------------- */
 

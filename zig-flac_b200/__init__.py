@@ -65,6 +65,19 @@ class ZfWavFormat(C.Structure):
 _LIB = None
 
 
+class ZfDecodeInfo(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("sample_rate", C.c_uint32), ("channels", C.c_uint32), ("bit_depth", C.c_uint32),
+                ("min_block_size", C.c_uint32), ("max_block_size", C.c_uint32), ("launches", C.c_uint32),
+                ("kernel_ms", C.c_float), ("samples_per_channel", C.c_uint64), ("streaminfo_samples", C.c_uint64),
+                ("pcm_bytes", C.c_uint64), ("n_frames", C.c_uint64), ("bad_frame", C.c_uint64),
+                ("bad_frame_status", C.c_uint32), ("md5_status", C.c_int32), ("md5", C.c_uint8 * 16)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k not in ("md5", "struct_size")}
+        d["md5"] = bytes(self.md5)
+        return d
+
+
 def build(force=False):
     """Compile the shared library in-tree with nvcc (sm_100a)."""
     spec = importlib.util.spec_from_file_location("_zf_build", os.path.join(_HERE, "build.py"))
@@ -136,6 +149,15 @@ def _lib():
     L.zf_host_free.argtypes = [vp]
     L.zf_host_free.restype = None
     L.zf_synth_pcm.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int]
+    L.zf_decoder_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.zf_decoder_destroy.argtypes = [vp]
+    L.zf_decoder_destroy.restype = None
+    L.zf_flac_stream_info.argtypes = [vp, C.c_size_t, C.POINTER(ZfDecodeInfo)]
+    L.zf_decode_flac.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.c_uint32, C.POINTER(ZfDecodeInfo)]
+    L.zf_decode_flac_device.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(ZfDecodeInfo)]
+    L.zf_decode_flac_memory.argtypes = [vp, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t),
+                                        C.POINTER(ZfDecodeInfo)]
+    L.zf_decode_flac_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint32]
     _LIB = L
     return L
 
@@ -472,3 +494,98 @@ class Wav8Reader:
 
 def device_available(device_id=0):
     return _lib().zf_device_check(device_id) == ZF_OK
+
+
+# ---- decoder (extension; the reference has none, readme.md:33) ----------------------------------------------------
+ZF_DECODE_CHECK_MD5 = 1
+ZF_DECODE_REQUIRE_MD5 = 2
+ZF_ERR_FLAC_FRAME = -34
+
+
+def flac_stream_info(flac_bytes):
+    """STREAMINFO of a FLAC stream (host only)."""
+    a = _u8(flac_bytes)
+    info = ZfDecodeInfo(struct_size=C.sizeof(ZfDecodeInfo))
+    rc = _lib().zf_flac_stream_info(a.ctypes.data, a.size, C.byref(info))
+    if rc != ZF_OK:
+        raise FlacGpuError(rc, "flac_stream_info")
+    return info.as_dict()
+
+
+class Decoder:
+    """FLAC decoder on the device (zf_decoder_*).  decode() returns (pcm bytes as uint8 array, info dict): interleaved
+    little-endian samples of bit_depth / 8 bytes, signed -- the layout Encoder.encode_pcm takes.  Raises FlacGpuError
+    without an sm_100 GPU (no CPU fallback) and on any damaged frame."""
+
+    def __init__(self, device_id=0):
+        h = C.c_void_p()
+        rc = _lib().zf_decoder_create(device_id, C.byref(h))
+        if rc != ZF_OK:
+            raise FlacGpuError(rc, "zf_decoder_create")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib().zf_decoder_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def decode(self, flac_bytes, out=None, check_md5=False, require_md5=False):
+        a = _u8(flac_bytes)
+        info = ZfDecodeInfo(struct_size=C.sizeof(ZfDecodeInfo))
+        flags = (ZF_DECODE_CHECK_MD5 if check_md5 else 0) | (ZF_DECODE_REQUIRE_MD5 if require_md5 else 0)
+        n = C.c_size_t()
+        if out is None:
+            rc = _lib().zf_decode_flac(self.handle, a.ctypes.data, a.size, None, 0, C.byref(n), 0, C.byref(info))
+            if rc != ZF_OK:
+                raise FlacGpuError(rc, "zf_decode_flac (sizes)")
+            out = np.empty(n.value, dtype=np.uint8)
+        rc = _lib().zf_decode_flac(self.handle, a.ctypes.data, a.size, out.ctypes.data, out.size, C.byref(n), flags, C.byref(info))
+        if rc != ZF_OK:
+            e = FlacGpuError(rc, "zf_decode_flac")
+            e.info = info.as_dict()
+            raise e
+        return out[:n.value], info.as_dict()
+
+    def decode_device(self, d_flac_ptr, flac_len, d_pcm_ptr, pcm_cap):
+        info = ZfDecodeInfo(struct_size=C.sizeof(ZfDecodeInfo))
+        n = C.c_size_t()
+        rc = _lib().zf_decode_flac_device(self.handle, d_flac_ptr, flac_len, d_pcm_ptr, pcm_cap, C.byref(n), C.byref(info))
+        if rc != ZF_OK:
+            e = FlacGpuError(rc, "zf_decode_flac_device")
+            e.info = info.as_dict()
+            raise e
+        return n.value, info.as_dict()
+
+
+def decode_flac(flac_bytes, device_id=0, check_md5=False, require_md5=False):
+    """zf_decode_flac_memory: one-shot decode -> (pcm uint8 array, info dict)."""
+    a = _u8(flac_bytes)
+    p = C.c_void_p()
+    n = C.c_size_t()
+    info = ZfDecodeInfo(struct_size=C.sizeof(ZfDecodeInfo))
+    flags = (ZF_DECODE_CHECK_MD5 if check_md5 else 0) | (ZF_DECODE_REQUIRE_MD5 if require_md5 else 0)
+    rc = _lib().zf_decode_flac_memory(a.ctypes.data, a.size, device_id, flags, C.byref(p), C.byref(n), C.byref(info))
+    if rc != ZF_OK:
+        e = FlacGpuError(rc, "zf_decode_flac_memory")
+        e.info = info.as_dict()
+        raise e
+    out = np.ctypeslib.as_array((C.c_uint8 * max(n.value, 1)).from_address(p.value))[:n.value].copy()
+    _lib().zf_free(p)
+    return out, info.as_dict()
+
+
+def decode_file(in_path, out_path, device_id=0, require_md5=True):
+    return _lib().zf_decode_flac_file(os.fsencode(in_path), os.fsencode(out_path), device_id,
+                                      ZF_DECODE_REQUIRE_MD5 if require_md5 else 0)

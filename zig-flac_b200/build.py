@@ -23,7 +23,7 @@ CLI = os.path.join(HERE, "flac")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
-CU = ["zf_capi.cu"]
+CU = ["zf_capi.cu", "zf_decode.cu"]
 CPP = ["zf_host.cpp", "zf_driver.cpp"]
 C_SRC = ["zf_synth.c"]
 

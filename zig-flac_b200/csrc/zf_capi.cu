@@ -581,6 +581,11 @@ int slot_collect(zf_encoder *e, Slot &sl, uint8_t *out, size_t out_cap, size_t *
 
 }  // namespace
 
+// zf_decode.cu reports through the same thread-local text (library-internal, not part of the ABI)
+__attribute__((visibility("hidden"))) void zf_internal_set_error(const char *msg) {
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s", msg);
+}
+
 extern "C" {
 
 const char *zf_last_cuda_error(void) { return g_cuda_err; }

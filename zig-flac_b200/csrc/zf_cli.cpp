@@ -1,6 +1,7 @@
 // zf_cli.cpp -- `flac in_file.wav out_file.flac` with the reference's argv / exit-code contract
 // (src/cli.zig:7-27: exit 1 on bad usage; src/cli/wav2flac.zig:24-27: exit 2 on an unsupported format).
-// Extra, optional: `--devices 0,1,2,3` shards the stream over several GPUs.
+// Extra, optional: `--devices 0,1,2,3` shards the stream over several GPUs; `-d in.flac out.wav` decodes (extension: the
+// reference has no decoder) and verifies every frame's CRC-16 and the STREAMINFO MD5.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -12,8 +13,11 @@
 int main(int argc, char **argv) {
     const char *input = nullptr, *output = nullptr;
     std::vector<int> devices;
+    bool decode = false;
     for (int i = 1; i < argc; i++) {
-        if (!strcmp(argv[i], "--devices") && i + 1 < argc) {
+        if (!strcmp(argv[i], "-d") || !strcmp(argv[i], "--decode")) {
+            decode = true;
+        } else if (!strcmp(argv[i], "--devices") && i + 1 < argc) {
             for (char *tok = strtok(argv[++i], ","); tok; tok = strtok(nullptr, ",")) devices.push_back(atoi(tok));
         } else if (!input) input = argv[i];
         else if (!output) output = argv[i];
@@ -21,6 +25,14 @@ int main(int argc, char **argv) {
     if (!input || !output) {
         fprintf(stderr, "error: usage: flac in_file.wav out_file.flac\n");  // cli.zig:18
         return 1;
+    }
+    if (decode) {
+        const int rc = zf_decode_flac_file(input, output, devices.empty() ? 0 : devices[0], ZF_DECODE_REQUIRE_MD5);
+        if (rc) {
+            fprintf(stderr, "error: %s (%d) %s\n", zf_strerror(rc), rc, zf_last_cuda_error());
+            return 3;
+        }
+        return 0;
     }
     const int rc = zf_encode_wav_file(input, output, devices.empty() ? nullptr : devices.data(), (int)devices.size());
     if (rc == 2) {

@@ -32,6 +32,11 @@ const char *zf_strerror(int status) {
         case ZF_ERR_WAV_NO_DATA: return "DataNotFound";
         case ZF_ERR_WAV_BIT_RATE: return "BitRateUnmatch";
         case ZF_ERR_WAV_INCOMPLETE: return "IncompleteStream";
+        case ZF_ERR_FLAC_NOT_FLAC: return "not a FLAC stream";
+        case ZF_ERR_FLAC_TRUNCATED: return "FLAC stream truncated";
+        case ZF_ERR_FLAC_FRAME: return "FLAC frame failed to decode";
+        case ZF_ERR_FLAC_COUNT: return "decoded sample count differs from STREAMINFO";
+        case ZF_ERR_FLAC_MD5: return "MD5 of the decoded samples differs from STREAMINFO";
         default: return "unknown status";
     }
 }
