@@ -27,13 +27,14 @@ template <typename ST>
 static int run(const uint8_t *s, const HostStreamInfo &si, const StreamParams &sp, const std::vector<uint64_t> &fpos,
                const std::vector<uint64_t> &first, uint8_t *pcm, size_t cap, uint32_t *bad) {
     const size_t n = first.size();
-    std::vector<ST> work((size_t)sp.channels * sp.max_block);
+    std::vector<ST> work((size_t)sp.channels * plane_stride(sp.max_block));
+    ST ring[8 * 32];
     uint16_t tab[256];
     for (uint32_t b = 0; b < 256; b++) tab[b] = (uint16_t)crc16_table_entry(b);
     const uint32_t bytes = si.bits / 8u, stride = si.channels * bytes;
     for (size_t f = 0; f < n; f++) {
         FrameRec rec;
-        decode_frame<ST>(s, fpos[f], fpos[f + 1], sp, work.data(), rec);
+        decode_frame<ST>(s, fpos[f], fpos[f + 1], sp, work.data(), ring + (f & 31), rec);
         if (rec.status == kOk) {  // zf_dec_crc16_kernel: 64 chunks
             const uint64_t begin = fpos[f], len = fpos[f + 1] - begin, chunk = (len + 63) / 64;
             const uint32_t xc = crc16_xpow8(chunk);
@@ -73,7 +74,7 @@ extern "C" long long emu_decode_flac(const uint8_t *flac, size_t len, uint8_t *p
     if (mrc) return mrc == -2 ? -33 : -32;
     info[0] = si.channels; info[1] = si.bits; info[2] = si.sample_rate; info[3] = 0;
     if (!(si.bits == 8 || si.bits == 16 || si.bits == 24 || si.bits == 32)) return -2;
-    std::vector<uint32_t> buf((len + 64 + 3) / 4, 0u);  // 4-byte aligned, zero bytes behind the stream
+    std::vector<uint32_t> buf((len + kStreamPad + 3) / 4, 0u);  // 4-byte aligned, zero bytes behind the stream
     uint8_t *s = reinterpret_cast<uint8_t *>(buf.data());
     memcpy(s, flac, len);
     StreamParams sp;

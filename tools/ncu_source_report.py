@@ -23,7 +23,7 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "zig-flac_b200", "libzigflac_b200.so")], cwd=tmp,
                capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.startswith("zf_capi")][0]
+cubin = [f for f in os.listdir(tmp) if f.startswith("zf_decode" if "zf_dec" in kern or "3dec" in kern else "zf_capi")][0]
 dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
 lines = dis.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith(".text.") and kern in l)

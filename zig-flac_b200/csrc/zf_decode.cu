@@ -71,6 +71,8 @@ int grow(T *&p, size_t &cap, size_t need) {
 
 struct zf_decoder {
     int device = 0;
+    int sm_count = 148;
+    uint32_t warps_per_sm = 12;  // frames kernel: warps per SM before the lanes of a warp are filled (ZF_DEC_WARPS_PER_SM)
     cudaStream_t stream = nullptr;  // upload, scan, tables
     cudaEvent_t ev_ready = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
     uint8_t *d_stream = nullptr;
@@ -131,8 +133,11 @@ int finish_slot(zf_decoder *d, DSlot &sl, zf_decode_info *info, float &kernel_ms
 template <typename ST>
 void launch_batch(zf_decoder *d, DSlot &sl, uint32_t first, uint32_t nb, const StreamParams &sp, uint8_t *pcm_base,
                   unsigned long long pcm_cap) {
-    zf::dec::zf_dec_frames_kernel<ST><<<(nb + 31u) / 32u, 32, 0, sl.stream>>>(d->d_stream, d->d_fpos + first, nb, sp,
-                                                                              static_cast<ST *>(sl.d_work), d->d_rec + first);
+    // lanes per warp: enough warps for a few per scheduler first (zf_dec_frames_kernel)
+    uint32_t lpw = 1;
+    while (lpw < 32u && (nb + lpw - 1u) / lpw > (uint32_t)d->sm_count * d->warps_per_sm) lpw *= 2u;
+    zf::dec::zf_dec_frames_kernel<ST><<<(nb + lpw - 1u) / lpw, 32, 0, sl.stream>>>(d->d_stream, d->d_fpos + first, nb, lpw, sp,
+                                                                                 static_cast<ST *>(sl.d_work), d->d_rec + first);
     zf::dec::zf_dec_crc16_kernel<<<nb, 64, 0, sl.stream>>>(d->d_stream, d->d_fpos + first, nb, d->d_rec + first);
     const dim3 grid((sp.max_block + 255u) / 256u, nb);
     zf::dec::zf_dec_output_kernel<ST><<<grid, 256, 0, sl.stream>>>(static_cast<const ST *>(sl.d_work), d->d_rec + first,
@@ -194,11 +199,11 @@ int decode_core(zf_decoder *d, const uint8_t *flac_host, const uint8_t *d_flac, 
     sp.max_block = si.max_block ? si.max_block : 65535u;
     sp.sample_rate = si.sample_rate;
 
-    // ---- stream to the device, 16 zero bytes behind it (the bit reader looks ahead) ----
-    if (grow(d->d_stream, d->stream_cap, len + 64)) return ZF_ERR_CUDA;
+    // ---- stream to the device, zero bytes behind it (the bit reader looks ahead) ----
+    if (grow(d->d_stream, d->stream_cap, len + zf::dec::kStreamPad)) return ZF_ERR_CUDA;
     ZFD_CUDA(cudaMemcpyAsync(d->d_stream, flac_host ? flac_host : d_flac, len, flac_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
                              d->stream));
-    ZFD_CUDA(cudaMemsetAsync(d->d_stream + len, 0, 64, d->stream));
+    ZFD_CUDA(cudaMemsetAsync(d->d_stream + len, 0, zf::dec::kStreamPad, d->stream));
 
     // ---- header scan ----
     const uint64_t expect_frames = si.total_samples && si.min_block ? si.total_samples / si.min_block + 2 : len / 64 + 2;
@@ -275,7 +280,7 @@ int decode_core(zf_decoder *d, const uint8_t *flac_host, const uint8_t *d_flac, 
 
     // ---- batches ----
     const bool wide = si.bits == 32;
-    const size_t plane = (size_t)si.channels * sp.max_block * (wide ? 8 : 4);
+    const size_t plane = (size_t)si.channels * (((size_t)sp.max_block + 7) & ~(size_t)7) * (wide ? 8 : 4);  // zf::dec::plane_stride
     uint32_t per_batch = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(kWorkBytesPerSlot / plane, 32), kMaxBatchFrames);
     if (n_frames <= per_batch) per_batch = (uint32_t)n_frames;                                   // one batch
     else if (n_frames < 2ull * per_batch) per_batch = (uint32_t)((n_frames + 1) / 2);          // two even ones
@@ -360,6 +365,11 @@ int zf_decoder_create(int device_id, zf_decoder **out) {
     zf_decoder *d = new (std::nothrow) zf_decoder();
     if (!d) return ZF_ERR_NOMEM;
     d->device = device_id;
+    cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+    if (const char *e = getenv("ZF_DEC_WARPS_PER_SM")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 64) d->warps_per_sm = (uint32_t)v;
+    }
     auto fail = [&](int code) {
         zf_decoder_destroy(d);
         return code;

@@ -62,6 +62,10 @@ struct FrameRec {
     uint8_t pad[3];
 };
 
+// samples between the channel planes of a frame in the work buffer: a multiple of eight, so that eight samples are
+// whole 32-byte sectors (the buffer itself is 256-byte aligned)
+ZF_DEVICE uint32_t plane_stride(uint32_t max_block) { return (max_block + 7u) & ~7u; }
+
 struct FrameHdr {
     unsigned long long number;
     uint32_t block_size, ch_code, bits, len, variable, channels;
@@ -132,22 +136,74 @@ ZF_DEVICE bool parse_header(const uint8_t *p, unsigned long long avail, const St
     return true;
 }
 
-// ---- bit reader over the big-endian stream, addressed by absolute bit position --------------------------------
-// `w` is the stream buffer as 32-bit words (4-byte aligned, at least 8 readable bytes behind the last stream byte).
+// ---- bit reader: a 64-bit shift window in registers over the big-endian stream -------------------------------
+// `w` points at the 16-byte group that holds the frame's first byte (the stream buffer is 16-byte aligned and has
+// kStreamPad readable bytes behind the last stream byte).  The window `acc` is left-aligned and always holds at
+// least 32 valid bits, so any field of up to 32 bits is a shift away; it is topped up one word at a time from a queue
+// of four words in registers, behind which the next four are already on their way (one 16-byte load per four words,
+// issued a whole queue ahead of its use: its latency overlaps the codes in between).  The serial
+// chain of a Rice code is  window -> count leading zeros -> add -> shift -> window.
+// Every lane of a warp walks its own frame, so some lane enters a new cache line in most iterations: lines are
+// requested two ahead of the read position (no destination register, hence no scoreboard to wait for).
+constexpr uint32_t kStreamPad = 256;  // zero bytes the caller keeps behind the stream
+
 struct BitR {
     const uint32_t *w;
-    unsigned long long bp, end;  // current and limiting bit position
+    unsigned long long acc;
+    uint32_t q0, q1, q2, q3;  // the next words to enter the window, as loaded (q0 first); byte-swapped on entry
+    uint4 nxt;                // the four words behind them: loaded a whole queue ahead of their use
+    uint32_t qn;              // words left in the queue (1..4)
+    int32_t nacc;             // valid bits in acc (32..64)
+    uint32_t nw;              // index of q0 in the frame's words
+    uint32_t wlimit;          // last word index the parse may need
+    uint32_t end;             // limiting bit position (relative to w)
     uint32_t err;
 
-    ZF_DEVICE uint32_t peek() const {  // the next 32 bits
-        const unsigned long long wi = bp >> 5;
-        const uint32_t sh = (uint32_t)bp & 31u;
-        const uint32_t a = dec_bswap(w[wi]), b = dec_bswap(w[wi + 1]);
-        return sh ? (a << sh) | (b >> (32u - sh)) : a;
+    ZF_DEVICE void start(const uint32_t *words, uint32_t bit, uint32_t end_bit) {  // words: 16-byte aligned
+        w = words;
+        end = end_bit;
+        wlimit = (end_bit >> 5) + 2u;
+        err = 0;
+        const uint32_t i = bit >> 5, sh = bit & 31u;
+        acc = (((unsigned long long)dec_bswap(w[i]) << 32) | dec_bswap(w[i + 1])) << sh;
+        nacc = 64 - (int32_t)sh;
+        nw = i + 2u;
+        const uint4 *w4 = reinterpret_cast<const uint4 *>(w);
+        const uint4 v = w4[nw >> 2];
+        const uint32_t k = nw & 3u;
+        q0 = k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w;
+        q1 = k == 0 ? v.y : k == 1 ? v.z : v.w;
+        q2 = k == 0 ? v.z : v.w;
+        q3 = v.w;
+        qn = 4u - k;
+        nxt = w4[(nw >> 2) + 1u];
     }
-    ZF_DEVICE void skip(uint32_t n) {
-        bp += n;
-        if (bp > end) { err = 1; bp = end; }
+    ZF_DEVICE uint32_t pos() const { return nw * 32u - (uint32_t)nacc; }  // bits consumed, relative to w
+    ZF_DEVICE uint32_t peek() const { return (uint32_t)(acc >> 32); }
+    ZF_DEVICE void skip(uint32_t n) {  // n <= 32
+        acc <<= n;
+        nacc -= (int32_t)n;
+        if (nacc < 32) {
+            acc |= (unsigned long long)dec_bswap(q0) << (32 - nacc);
+            nacc += 32;
+            nw++;
+            q0 = q1; q1 = q2; q2 = q3;
+            if (--qn == 0u) {  // nw is a multiple of four here
+                q0 = nxt.x; q1 = nxt.y; q2 = nxt.z; q3 = nxt.w;
+                qn = 4u;
+                if ((nw & 31u) == 0u) {  // once per 128 bytes: the limit (a damaged frame must not lead the reader out of
+                                         // the buffer: it goes round in the last words it may touch) and the prefetch
+                    if (nw > wlimit) {
+                        err = 1;
+                        nw -= 32u;
+                    }
+#ifndef ZF_HOST_EMU
+                    else if (nw + 64u <= wlimit) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + nw + 64u));
+#endif
+                }
+                nxt = reinterpret_cast<const uint4 *>(w)[(nw >> 2) + 1u];
+            }
+        }
     }
     ZF_DEVICE uint32_t read(uint32_t n) {  // n <= 32
         if (n == 0) return 0;
@@ -181,29 +237,58 @@ struct BitR {
             if (err) return q;
         }
     }
+    ZF_DEVICE bool overrun() const { return err != 0 || pos() > end; }
 };
 
 // One subframe (RFC 9639 section 9.2) of `bs` samples at `bps` bits into out[0 .. bs).  ST = int32_t for streams of
 // up to 24-bit samples (a side channel has 25), long long for 32-bit streams (33).  Samples are stored BEFORE the
 // wasted-bits shift (the predictor runs on them); the shift count goes to `wasted`.
+//
+// `ring` is this lane's column of an 8 x 32 staging array in shared memory (element k at ring[32 k]).  A lane that wrote
+// every sample straight to its own plane would re-use the store's source register one iteration later and wait each
+// time until the 32-address store has been taken apart; FIXED subframes therefore collect eight samples and write them
+// as whole 32-byte sectors.
 template <typename ST>
-ZF_DEVICE uint32_t decode_subframe(BitR &br, ST *out, uint32_t bs, uint32_t bps, uint8_t &wasted_out) {
+ZF_DEVICE void flush8(ST *dst, const ST *ring) {
+    ST v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = ring[32 * k];
+#ifdef ZF_HOST_EMU
+    for (int k = 0; k < 8; k++) dst[k] = v[k];
+#else
+    if (sizeof(ST) == 4) {
+        uint4 *d = reinterpret_cast<uint4 *>(dst);
+        d[0] = make_uint4((uint32_t)v[0], (uint32_t)v[1], (uint32_t)v[2], (uint32_t)v[3]);
+        d[1] = make_uint4((uint32_t)v[4], (uint32_t)v[5], (uint32_t)v[6], (uint32_t)v[7]);
+    } else {
+        ulonglong2 *d = reinterpret_cast<ulonglong2 *>(dst);
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = make_ulonglong2((unsigned long long)v[2 * k], (unsigned long long)v[2 * k + 1]);
+    }
+#endif
+}
+
+template <typename ST>
+ZF_DEVICE uint32_t decode_subframe(BitR &br, ST *out, ST *ring, uint32_t bs, uint32_t bps, uint8_t &wasted_out) {
     if (br.read(1)) return kErrReserved;
     const uint32_t type = br.read(6);
     uint32_t wasted = 0;
     if (br.read(1)) wasted = br.read_unary() + 1u;
     wasted_out = (uint8_t)wasted;
-    if (br.err) return kErrOverrun;
+    if (br.overrun()) return kErrOverrun;
     if (wasted >= bps) return kErrRange;
     bps -= wasted;
     if (type == 0) {  // CONSTANT
         const ST v = (ST)br.read_signed(bps);
         for (uint32_t i = 0; i < bs; i++) out[i] = v;
-        return br.err ? kErrOverrun : kOk;
+        return br.overrun() ? kErrOverrun : kOk;
     }
     if (type == 1) {  // VERBATIM
-        for (uint32_t i = 0; i < bs; i++) out[i] = (ST)br.read_signed(bps);
-        return br.err ? kErrOverrun : kOk;
+        for (uint32_t i = 0; i < bs; i++) {
+            out[i] = (ST)br.read_signed(bps);
+            if (br.err) return kErrOverrun;
+        }
+        return br.overrun() ? kErrOverrun : kOk;
     }
     uint32_t order, shift = 0;
     bool lpc = false;
@@ -234,67 +319,74 @@ ZF_DEVICE uint32_t decode_subframe(BitR &br, ST *out, uint32_t bs, uint32_t bps,
     const uint32_t psize = bs >> po;
     if (po && (psize << po) != bs) return kErrRange;
     if (psize < order) return kErrRange;
-    if (br.err) return kErrOverrun;
-    // FIXED predictors as difference operators: four history registers, binomial coefficients by order
-    ST h1 = 0, h2 = 0, h3 = 0, h4 = 0;
-    if (!lpc) {
-        if (order >= 1) h1 = out[order - 1];
-        if (order >= 2) h2 = out[order - 2];
-        if (order >= 3) h3 = out[order - 3];
-        if (order >= 4) h4 = out[order - 4];
-    }
-    const ST c1 = order == 0 ? 0 : (ST)order;
-    const ST c2 = order == 2 ? -1 : order == 3 ? -3 : order == 4 ? -6 : 0;
-    const ST c3 = order == 3 ? 1 : order == 4 ? 4 : 0;
-    const ST c4 = order == 4 ? -1 : 0;
-    uint32_t part_end = order;  // "a partition ends here": the first parameter is read in front of sample `order`
-    uint32_t next_end = psize;
+    if (br.overrun()) return kErrOverrun;
+    // One flat loop over the sample index for all lanes of the warp (their partition sizes differ: a change of
+    // partition is a short divergent branch, not a loop boundary).  "A partition ends here": the first parameter is
+    // read in front of sample `order`.
+    uint32_t part_end = order, next_end = psize;
     uint32_t k = 0, raw = 0;
     bool esc = false;
-    for (uint32_t i = order; i < bs; i++) {
-        if (i == part_end) {
-            k = br.read(plen);
-            esc = k == escape;
-            if (esc) raw = br.read(5);
-            part_end = next_end;
-            next_end += psize;
-        }
-        ST r;
-        if (esc) {
-            r = (ST)br.read_signed(raw);
-        } else {
-            const uint32_t v = br.peek();
-            uint32_t zz;
-            const uint32_t lz = (uint32_t)__clz((int)v);
-            if (v != 0 && lz + 1u + k <= 32u) {  // the whole code lies in the window
-                const uint32_t rem = k ? ((v << lz) << 1) >> (32u - k) : 0u;
-                zz = (lz << k) | rem;
-                br.skip(lz + 1u + k);
-            } else {
-                const uint32_t q = br.read_unary();
-                zz = (q << k) | br.read(k);
-            }
-            r = (ST)(int32_t)((zz >> 1) ^ (0u - (zz & 1u)));
-        }
-        ST x;
-        if (lpc) {
-            long long acc = 0;
-            for (uint32_t j = 0; j < order; j++) acc += (long long)coef[j] * (long long)out[i - 1 - j];
-            x = r + (ST)(acc >> shift);
-        } else {
-            x = r + c1 * h1 + c2 * h2 + c3 * h3 + c4 * h4;
-            h4 = h3; h3 = h2; h2 = h1; h1 = x;
-        }
-        out[i] = x;
-        if (br.err) return kErrOverrun;
+#define ZF_DEC_RESIDUAL(R)                                                                       \
+    if (i == part_end) {                                                                         \
+        k = br.read(plen);                                                                       \
+        esc = k == escape;                                                                       \
+        if (esc) raw = br.read(5);                                                               \
+        part_end = next_end;                                                                     \
+        next_end += psize;                                                                       \
+    }                                                                                            \
+    ST R;                                                                                        \
+    if (esc) {                                                                                   \
+        R = (ST)br.read_signed(raw);                                                             \
+    } else {                                                                                     \
+        const uint32_t v = br.peek();                                                            \
+        uint32_t zz;                                                                             \
+        const uint32_t lz = (uint32_t)__clz((int)v);                                             \
+        if (v != 0 && lz + 1u + k <= 32u) { /* the whole code lies in the window */              \
+            const uint32_t rem = k ? ((v << lz) << 1) >> (32u - k) : 0u;                         \
+            zz = (lz << k) | rem;                                                                \
+            br.skip(lz + 1u + k);                                                                \
+        } else {                                                                                 \
+            const uint32_t q = br.read_unary();                                                  \
+            zz = (q << k) | br.read(k);                                                          \
+        }                                                                                        \
+        R = (ST)(int32_t)((zz >> 1) ^ (0u - (zz & 1u)));                                         \
     }
-    return br.err ? kErrOverrun : kOk;
+    if (lpc) {
+        for (uint32_t i = order; i < bs; i++) {
+            ZF_DEC_RESIDUAL(r)
+            long long sum = 0;
+            for (uint32_t j = 0; j < order; j++) sum += (long long)coef[j] * (long long)out[i - 1 - j];
+            out[i] = r + (ST)(sum >> shift);
+        }
+    } else {
+        // FIXED predictors as running differences: d_j is the j-th difference of the signal at the previous sample; a
+        // level above the order passes the residual through (its mask is 0), so one piece of code serves orders 0..4
+        ST d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        if (order >= 1) d0 = out[order - 1];
+        if (order >= 2) d1 = out[order - 1] - out[order - 2];
+        if (order >= 3) d2 = out[order - 1] - 2 * out[order - 2] + out[order - 3];
+        if (order >= 4) d3 = out[order - 1] - 3 * out[order - 2] + 3 * out[order - 3] - out[order - 4];
+        const ST m0 = order > 0 ? -1 : 0, m1 = order > 1 ? -1 : 0, m2 = order > 2 ? -1 : 0, m3 = order > 3 ? -1 : 0;
+        for (uint32_t i = 0; i < order; i++) ring[32u * (i & 7u)] = out[i];  // the warm-ups join the first sector
+        for (uint32_t i = order; i < bs; i++) {
+            ZF_DEC_RESIDUAL(r)
+            d3 = (d3 & m3) + r;
+            d2 = (d2 & m2) + d3;
+            d1 = (d1 & m1) + d2;
+            d0 = (d0 & m0) + d1;
+            ring[32u * (i & 7u)] = d0;
+            if ((i & 7u) == 7u) flush8<ST>(out + (i - 7u), ring);
+        }
+        for (uint32_t i = bs & ~7u; i < bs; i++) out[i] = ring[32u * (i & 7u)];
+    }
+#undef ZF_DEC_RESIDUAL
+    return br.overrun() ? kErrOverrun : kOk;
 }
 
 // One frame: header, subframes, padding; stream bytes [begin, end) with the CRC-16 in the last two.
 template <typename ST>
 ZF_DEVICE void decode_frame(const uint8_t *s, unsigned long long begin, unsigned long long end, const StreamParams &sp,
-                            ST *work, FrameRec &rec) {
+                            ST *work, ST *ring, FrameRec &rec) {
     rec.block_size = 0;
     rec.ch_code = 0;
     for (int c = 0; c < 8; c++) rec.wasted[c] = 0;
@@ -307,20 +399,19 @@ ZF_DEVICE void decode_frame(const uint8_t *s, unsigned long long begin, unsigned
     rec.block_size = h.block_size;
     rec.ch_code = (uint8_t)h.ch_code;
     BitR br;
-    br.w = reinterpret_cast<const uint32_t *>(s);
-    br.bp = (begin + h.len) * 8ull;
-    br.end = (end - 2) * 8ull;
-    br.err = 0;
+    const uint32_t lead = (uint32_t)(begin & 15ull) * 8u;  // bits between the 16-byte boundary and the frame's first byte
+    br.start(reinterpret_cast<const uint32_t *>(s + (begin & ~15ull)), lead + h.len * 8u, lead + (uint32_t)(end - 2 - begin) * 8u);
     uint32_t st = kOk;
     for (uint32_t c = 0; c < h.channels && st == kOk; c++) {
         const bool side = (h.ch_code == 8u && c == 1) || (h.ch_code == 9u && c == 0) || (h.ch_code == 10u && c == 1);
-        st = decode_subframe<ST>(br, work + (size_t)c * sp.max_block, h.block_size, h.bits + (side ? 1u : 0u), rec.wasted[c]);
+        st = decode_subframe<ST>(br, work + (size_t)c * plane_stride(sp.max_block), ring, h.block_size, h.bits + (side ? 1u : 0u),
+                                 rec.wasted[c]);
     }
     if (st == kOk) {
-        const uint32_t padbits = (8u - ((uint32_t)br.bp & 7u)) & 7u;
+        const uint32_t padbits = (8u - (br.pos() & 7u)) & 7u;
         if (padbits && br.read(padbits) != 0) st = kErrPadding;
-        else if (br.err) st = kErrOverrun;
-        else if (br.bp != br.end) st = kErrLength;
+        else if (br.overrun()) st = kErrOverrun;
+        else if (br.pos() != br.end) st = kErrLength;
     }
     rec.status = st;
 }
@@ -361,7 +452,7 @@ template <typename ST>
 ZF_DEVICE bool restore_sample(const ST *work, uint32_t max_block, uint32_t i, const FrameRec &rec, uint32_t channels,
                               uint32_t bits, long long (&v)[8]) {
     for (uint32_t c = 0; c < channels; c++)
-        v[c] = (long long)((unsigned long long)(long long)work[(size_t)c * max_block + i] << rec.wasted[c]);
+        v[c] = (long long)((unsigned long long)(long long)work[(size_t)c * plane_stride(max_block) + i] << rec.wasted[c]);
     if (rec.ch_code == 8u) {
         v[1] = v[0] - v[1];
     } else if (rec.ch_code == 9u) {
@@ -410,14 +501,17 @@ __global__ void __launch_bounds__(256) zf_dec_scan_kernel(const uint8_t *s, unsi
     }
 }
 
-// one thread per frame
+// One thread per frame, `lpw` of them in a warp (the other lanes leave at once).  Every lane walks its own frame, so
+// with 32 busy lanes some lane misses the L1 cache in most iterations and the whole warp waits for L2; the host
+// therefore spreads the frames over as many warps as the device holds (a few per scheduler) before it fills the lanes.
 template <typename ST>
 __global__ void __launch_bounds__(32) zf_dec_frames_kernel(const uint8_t *s, const unsigned long long *fpos, uint32_t n_frames,
-                                                           StreamParams sp, ST *work, FrameRec *rec) {
-    const uint32_t f = blockIdx.x * 32u + threadIdx.x;
-    if (f >= n_frames) return;
+                                                           uint32_t lpw, StreamParams sp, ST *work, FrameRec *rec) {
+    __shared__ ST ring[8 * 32];
+    const uint32_t f = blockIdx.x * lpw + threadIdx.x;
+    if (threadIdx.x >= lpw || f >= n_frames) return;
     FrameRec r;
-    decode_frame<ST>(s, fpos[f], fpos[f + 1], sp, work + (size_t)f * sp.channels * sp.max_block, r);
+    decode_frame<ST>(s, fpos[f], fpos[f + 1], sp, work + (size_t)f * sp.channels * plane_stride(sp.max_block), ring + threadIdx.x, r);
     rec[f] = r;
 }
 
@@ -459,7 +553,7 @@ __global__ void __launch_bounds__(256) zf_dec_output_kernel(const ST *work, Fram
     const uint32_t n = r.block_size - i0 < 256u ? r.block_size - i0 : 256u;
     if (t < n) {
         long long v[8];
-        if (!restore_sample<ST>(work + (size_t)f * sp.channels * sp.max_block, sp.max_block, i0 + t, r, sp.channels, sp.bits, v))
+        if (!restore_sample<ST>(work + (size_t)f * sp.channels * plane_stride(sp.max_block), sp.max_block, i0 + t, r, sp.channels, sp.bits, v))
             rec[f].status = kErrRange;  // benign race: every writer stores the same value
         for (uint32_t c = 0; c < sp.channels; c++)
             for (uint32_t k = 0; k < bytes; k++) stage[t * stride + c * bytes + k] = (uint8_t)((unsigned long long)v[c] >> (8u * k));
