@@ -54,6 +54,12 @@ def test_no_cpu_fallback(zf):
     assert ei.value.status == zf.ZF_ERR_NO_DEVICE
     rc, out = zf.wav_to_flac(_wav(zf, 16))
     assert rc == zf.ZF_ERR_NO_DEVICE and out is None
+    with pytest.raises(zf.FlacGpuError) as e:  # the decoder too
+        zf.Decoder()
+    assert e.value.status == zf.ZF_ERR_NO_DEVICE
+    with pytest.raises(zf.FlacGpuError) as e:
+        zf.decode_flac(b"fLaC" + bytes(100))
+    assert e.value.status == zf.ZF_ERR_NO_DEVICE
 
 
 def test_product_does_not_link_the_oracle(zf):

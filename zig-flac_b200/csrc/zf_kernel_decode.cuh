@@ -21,8 +21,8 @@
 //   zf_dec_output_kernel   one CTA per 256 samples of a frame: wasted-bits shift, inter-channel restore, range check,
 //                          interleave, little-endian packing through shared memory, coalesced stores.
 //
-// The independent CPU decoder oracle/flac_decode.c is the checker for this file (tests/test_gpu_decode.py); the two
-// share no code.
+// The test suite's independent CPU decoder is the checker for this file (tests/test_gpu_decode.py, and
+// tests/test_decode_emu.py for the device functions compiled for the host); the two share no code.
 #pragma once
 #include <stdint.h>
 
