@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-file", action="store_true", help="skip the whole-file (WAV -> FLAC, MD5 included) leg")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decoder leg")
     ap.add_argument("--profile", action="store_true", help="device-resident steps only (for runs under ncu)")
     return ap.parse_args()
 
@@ -417,6 +418,45 @@ def main():
     except Exception as exc:  # the whole-file leg is an extra: never lose the bench line over it
         e2e_file = {"error": repr(exc)}
 
+    # ---- decoder (extension, N = 1): this step's frames as a FLAC stream -> PCM, device-resident (FLAC and PCM in HBM)
+    #      and from / to pinned host buffers; the result must be the PCM that went in ----
+    decode = None
+    try:
+        if world == 1 and not args.no_decode and LPC_ORDER.get(args.workload, 0) == 0:
+            si = zf.StreamInfo(rate, CHANNELS, bits, nsamples)
+            stream_bytes = np.concatenate([np.frombuffer(b"fLaC" + bytes([0x80, 0, 0, 34]) + bytes(si.bytes()), dtype=np.uint8), got])
+            h_flac = torch.empty(stream_bytes.size, dtype=torch.uint8, pin_memory=True)
+            h_flac.numpy()[:] = stream_bytes
+            d_flac = h_flac.to(dev)
+            d_dec = torch.zeros(pcm_bytes, dtype=torch.uint8, device=dev)
+            h_dec = torch.empty(pcm_bytes, dtype=torch.uint8, pin_memory=True)
+            with zf.Decoder(local_rank) as dec:
+                for _ in range(2):
+                    nb, dinfo = dec.decode_device(d_flac.data_ptr(), d_flac.numel(), d_dec.data_ptr(), d_dec.numel())
+                torch.cuda.synchronize(dev)
+                dsteps = 5
+                t0 = time.perf_counter()
+                for _ in range(dsteps):
+                    nb, dinfo = dec.decode_device(d_flac.data_ptr(), d_flac.numel(), d_dec.data_ptr(), d_dec.numel())
+                torch.cuda.synchronize(dev)
+                dev_s = (time.perf_counter() - t0) / dsteps
+                dec.decode(h_flac.numpy(), out=h_dec.numpy())
+                t0 = time.perf_counter()
+                for _ in range(dsteps):
+                    dgot, dinfo2 = dec.decode(h_flac.numpy(), out=h_dec.numpy())
+                host_s = (time.perf_counter() - t0) / dsteps
+            decode = {"value": round(nsamples * CHANNELS / dev_s / 1e6, 2), "unit": UNIT, "ms_per_stream": round(dev_s * 1e3, 3),
+                      "kernel_ms": round(dinfo["kernel_ms"], 3), "launches": dinfo["launches"], "frames": dinfo["n_frames"],
+                      "e2e": {"value": round(nsamples * CHANNELS / host_s / 1e6, 2), "unit": UNIT, "ms_per_stream": round(host_s * 1e3, 3),
+                              "h2d_bytes": int(stream_bytes.size), "d2h_bytes": pcm_bytes},
+                      "roundtrip_equals_input": bool(nb == pcm_bytes and torch.equal(d_dec, d_pcm) and bool((dgot == h_pcm_np).all())),
+                      "api": "zf_decode_flac_device / zf_decode_flac (scan | one thread per frame | CRC-16 | restore + interleave)",
+                      "note": "extension (the reference has no decoder); wall clock of the blocking call, the frame table's round trip "
+                              "to the host included; bound by the latency of the serial bit parse of a frame (DESIGN.md section 9)"}
+            del d_flac, d_dec, h_dec
+    except Exception as exc:  # an extra: never lose the bench line over it
+        decode = {"error": repr(exc)}
+
     # the device-resident result and the host-path result are the same bytes
     same = bool((d_out[:flac_bytes].cpu().numpy() == got).all()) and flac_bytes == int(got.size)
 
@@ -461,6 +501,7 @@ def main():
                     "copy_ceiling_ms": round(copy_s * 1e3, 3), "frac_of_copy_ceiling": round(copy_s / e2e_s, 4),
                     "api": "zf_encode_pcm (pinned host PCM in, pinned host FLAC out, 2048-frame batches, pipeline: upload | encode | download on three streams)"},
             "e2e_file": e2e_file,
+            "decode": decode,
             "gpu_launches": all_launches,  # all ranks, timed region of the device-resident arm
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": (ncu or {}).get("dram_bytes_per_launch"),

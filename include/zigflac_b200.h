@@ -288,6 +288,11 @@ int zf_decode_flac_memory(const uint8_t *flac, size_t len, int device_id, uint32
                           zf_decode_info *info);
 /* `flac -d in.flac out.wav`: canonical PCM WAV (8-bit samples become unsigned, as WAV stores them). */
 int zf_decode_flac_file(const char *in_path, const char *out_path, int device_id, uint32_t flags);
+/* `flac -V in.wav out.flac` (verify after encoding): decodes out_path on the device and compares the samples with the `data`
+ * chunk of in_path byte for byte, CRC-16 of every frame and the STREAMINFO MD5 included.  ZF_OK, ZF_ERR_FLAC_* from the
+ * decoder, or ZF_ERR_FLAC_MD5 when the decoded samples differ from the WAV's.  (8-bit WAV goes through the reference
+ * reader's conversion, zf_wav8_to_samples, before the comparison.) */
+int zf_verify_flac_file(const char *wav_path, const char *flac_path, int device_id);
 
 /* ---- benchmark / test utility --------------------------------------------------------------------------- */
 

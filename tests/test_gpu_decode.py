@@ -107,6 +107,27 @@ def test_decode_whole_files_md5_and_entries(zf, oracle, dec, tmp_path):
         r = subprocess.run([os.path.join(ROOT, "zig-flac_b200", "flac"), "-d", str(fin), str(fcli)], capture_output=True)
         assert r.returncode == 0, r.stderr
         assert fcli.read_bytes() == wav
+        # verify after encoding: library entry and `flac -V in.wav out.flac`
+        fw = tmp_path / "in.wav"
+        fw.write_bytes(wav)
+        assert zf.verify_file(str(fw), str(fin)) == 0
+        fv = tmp_path / "v.flac"
+        r = subprocess.run([os.path.join(ROOT, "zig-flac_b200", "flac"), "-V", str(fw), str(fv)], capture_output=True)
+        assert r.returncode == 0, r.stderr
+        assert fv.read_bytes() == flac
+        other = bytearray(wav)
+        other[-1] ^= 1  # a WAV that differs in one bit from what the stream holds
+        fo = tmp_path / "other.wav"
+        fo.write_bytes(bytes(other))
+        assert zf.verify_file(str(fo), str(fin)) == -36
+    # 8-bit: the stream holds what the reference reader makes of the bytes (wav_reader.zig:71-88); verify knows
+    raw8 = (np.arange(9000) * 7 % 256).astype(np.uint8)
+    w8 = oracle.make_wav(raw8, 2, 8, 22050)
+    rc, f8 = zf.wav_to_flac(w8)
+    assert rc == 0
+    (tmp_path / "e.wav").write_bytes(w8)
+    (tmp_path / "e.flac").write_bytes(f8)
+    assert zf.verify_file(str(tmp_path / "e.wav"), str(tmp_path / "e.flac")) == 0
     # MD5 mismatch is reported
     bad = bytearray(flac)
     bad[30] ^= 0xFF  # inside STREAMINFO's MD5

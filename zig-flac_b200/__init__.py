@@ -158,6 +158,7 @@ def _lib():
     L.zf_decode_flac_memory.argtypes = [vp, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t),
                                         C.POINTER(ZfDecodeInfo)]
     L.zf_decode_flac_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint32]
+    L.zf_verify_flac_file.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
     _LIB = L
     return L
 
@@ -589,3 +590,8 @@ def decode_flac(flac_bytes, device_id=0, check_md5=False, require_md5=False):
 def decode_file(in_path, out_path, device_id=0, require_md5=True):
     return _lib().zf_decode_flac_file(os.fsencode(in_path), os.fsencode(out_path), device_id,
                                       ZF_DECODE_REQUIRE_MD5 if require_md5 else 0)
+
+
+def verify_file(wav_path, flac_path, device_id=0):
+    """zf_verify_flac_file: decode flac_path on the device and compare with the samples of wav_path."""
+    return _lib().zf_verify_flac_file(os.fsencode(wav_path), os.fsencode(flac_path), device_id)

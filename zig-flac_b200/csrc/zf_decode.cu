@@ -510,4 +510,50 @@ int zf_decode_flac_file(const char *in_path, const char *out_path, int device_id
     return ok && closed ? ZF_OK : ZF_ERR_IO;
 }
 
+static int read_file(const char *path, std::vector<uint8_t> &out) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return ZF_ERR_IO;
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long sz = ftell(f);
+        if (sz > 0) out.resize((size_t)sz);
+        fseek(f, 0, SEEK_SET);
+    }
+    const size_t got = out.empty() ? 0 : fread(out.data(), 1, out.size(), f);
+    fclose(f);
+    return got == out.size() ? ZF_OK : ZF_ERR_IO;
+}
+
+int zf_verify_flac_file(const char *wav_path, const char *flac_path, int device_id) {
+    if (!wav_path || !flac_path) return ZF_ERR_INVALID_ARG;
+    std::vector<uint8_t> wav, flac;
+    int rc = read_file(wav_path, wav);
+    if (rc == ZF_OK) rc = read_file(flac_path, flac);
+    if (rc) return rc;
+    zf_wav_format fmt;
+    rc = zf_wav_parse(wav.data(), wav.size(), &fmt);
+    if (rc) return rc;
+    uint8_t *pcm = nullptr;
+    size_t pcm_len = 0;
+    zf_decode_info info;
+    memset(&info, 0, sizeof info);
+    info.struct_size = sizeof info;
+    // 8-bit streams carry the MD5 of the raw file bytes (upstream's reader): compared below instead
+    rc = zf_decode_flac_memory(flac.data(), flac.size(), device_id, fmt.bit_depth == 8 ? 0u : ZF_DECODE_REQUIRE_MD5, &pcm, &pcm_len, &info);
+    if (rc) return rc;
+    const size_t want = (size_t)fmt.samples_count * fmt.channels * fmt.bytes_per_sample;
+    const uint8_t *data = wav.data() + fmt.data_offset;
+    bool same = pcm_len == want && info.channels == fmt.channels && info.bit_depth == fmt.bit_depth;
+    if (same && fmt.bit_depth == 8) {
+        std::vector<uint8_t> state((size_t)info.max_block_size * fmt.channels);
+        std::vector<int8_t> conv(want);
+        zf_wav8_state_init(state.data(), state.size());
+        zf_wav8_to_samples(data, fmt.samples_count, fmt.channels, info.max_block_size, 0, state.data(), conv.data());
+        same = memcmp(conv.data(), pcm, want) == 0;
+    } else if (same) {
+        same = memcmp(data, pcm, want) == 0;
+    }
+    free(pcm);
+    return same ? ZF_OK : ZF_ERR_FLAC_MD5;
+}
+
 }  // extern "C"
