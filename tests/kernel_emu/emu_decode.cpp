@@ -29,8 +29,8 @@ static int run(const uint8_t *s, const HostStreamInfo &si, const StreamParams &s
     const size_t n = first.size();
     std::vector<ST> work((size_t)sp.channels * plane_stride(sp.max_block));
     ST ring[8 * 32];
-    uint16_t tab[256];
-    for (uint32_t b = 0; b < 256; b++) tab[b] = (uint16_t)crc16_table_entry(b);
+    uint16_t tab[4][256];
+    for (uint32_t b = 0; b < 256; b++) crc16_build_tables(tab, b);
     const uint32_t bytes = si.bits / 8u, stride = si.channels * bytes;
     for (size_t f = 0; f < n; f++) {
         FrameRec rec;
@@ -42,7 +42,7 @@ static int run(const uint8_t *s, const HostStreamInfo &si, const StreamParams &s
             uint64_t done = 0;
             for (uint32_t k = 0; k < 64 && done < len; k++) {
                 const uint64_t m = len - done < chunk ? len - done : chunk;
-                c = crc16_mulmod(c, m == chunk ? xc : crc16_xpow8(m)) ^ crc16_bytes(s + begin + done, m, tab);
+                c = crc16_mulmod(c, m == chunk ? xc : crc16_xpow8(m)) ^ crc16_span(s + begin + done, m, tab);
                 done += m;
             }
             if (c != 0) rec.status = kErrCrc16;

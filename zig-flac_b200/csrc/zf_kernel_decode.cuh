@@ -439,10 +439,27 @@ ZF_DEVICE uint32_t crc16_table_entry(uint32_t b) {
     for (int k = 0; k < 8; k++) c = (c & 0x8000u) ? ((c << 1) ^ 0x8005u) & 0xffffu : (c << 1);
     return c;
 }
-ZF_DEVICE uint32_t crc16_bytes(const uint8_t *p, unsigned long long n, const uint16_t *tab) {
+// tab[k][v] = v * x^(8 k + 16) mod P, k = 0..3: table k + 1 is table k advanced by one zero byte
+// CRC-16 of n bytes at p (init 0): bytes up to a 4-byte boundary, then whole words four table look-ups at a time
+// (state c = c_hi x^8 + c_lo joins the first two bytes: c x^32 + b0 x^40 + b1 x^32 + b2 x^24 + b3 x^16), then the rest
+ZF_DEVICE uint32_t crc16_span(const uint8_t *p, unsigned long long n, const uint16_t (*tab)[256]) {
     uint32_t c = 0;
-    for (unsigned long long i = 0; i < n; i++) c = ((c << 8) & 0xffffu) ^ tab[((c >> 8) ^ p[i]) & 0xffu];
+    unsigned long long i = 0;
+    for (; i < n && (((uintptr_t)(p + i)) & 3u) != 0; i++) c = ((c << 8) & 0xffffu) ^ tab[0][((c >> 8) ^ p[i]) & 0xffu];
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(p + i);  // little-endian load: byte k of the stream in bits 8k..
+        c = tab[3][((c >> 8) ^ w) & 0xffu] ^ tab[2][(c ^ (w >> 8)) & 0xffu] ^ tab[1][(w >> 16) & 0xffu] ^ tab[0][w >> 24];
+    }
+    for (; i < n; i++) c = ((c << 8) & 0xffffu) ^ tab[0][((c >> 8) ^ p[i]) & 0xffu];
     return c;
+}
+ZF_DEVICE void crc16_build_tables(uint16_t (*tab)[256], uint32_t b) {  // entry b of the four tables
+    uint32_t v = crc16_table_entry(b);
+    tab[0][b] = (uint16_t)v;
+    for (int k = 1; k < 4; k++) {
+        v = ((v << 8) & 0xffffu) ^ crc16_table_entry(v >> 8);
+        tab[k][b] = (uint16_t)v;
+    }
 }
 
 // ---- output: one inter-channel sample ----------------------------------------------------------------------
@@ -518,15 +535,15 @@ __global__ void __launch_bounds__(32) zf_dec_frames_kernel(const uint8_t *s, con
 // one CTA (64 threads) per frame
 __global__ void __launch_bounds__(64) zf_dec_crc16_kernel(const uint8_t *s, const unsigned long long *fpos, uint32_t n_frames,
                                                           FrameRec *rec) {
-    __shared__ uint16_t tab[256];
+    __shared__ uint16_t tab[4][256];
     __shared__ uint32_t part[64];
     const uint32_t f = blockIdx.x, t = threadIdx.x;
-    for (uint32_t b = t; b < 256u; b += 64u) tab[b] = (uint16_t)crc16_table_entry(b);
+    for (uint32_t b = t; b < 256u; b += 64u) crc16_build_tables(tab, b);
     __syncthreads();
     const unsigned long long begin = fpos[f], n = fpos[f + 1] - begin;
     const unsigned long long chunk = (n + 63ull) / 64ull;
     const unsigned long long lo = chunk * t < n ? chunk * t : n, hi = lo + chunk < n ? lo + chunk : n;
-    part[t] = crc16_bytes(s + begin + lo, hi - lo, tab);
+    part[t] = crc16_span(s + begin + lo, hi - lo, tab);
     __syncthreads();
     if (t == 0) {
         const uint32_t xc = crc16_xpow8(chunk);
@@ -551,19 +568,61 @@ __global__ void __launch_bounds__(256) zf_dec_output_kernel(const ST *work, Fram
     if (r.status != kOk || i0 >= r.block_size) return;
     const uint32_t bytes = sp.bits / 8u, stride = sp.channels * bytes;
     const uint32_t n = r.block_size - i0 < 256u ? r.block_size - i0 : 256u;
-    if (t < n) {
-        long long v[8];
-        if (!restore_sample<ST>(work + (size_t)f * sp.channels * plane_stride(sp.max_block), sp.max_block, i0 + t, r, sp.channels, sp.bits, v))
-            rec[f].status = kErrRange;  // benign race: every writer stores the same value
-        for (uint32_t c = 0; c < sp.channels; c++)
-            for (uint32_t k = 0; k < bytes; k++) stage[t * stride + c * bytes + k] = (uint8_t)((unsigned long long)v[c] >> (8u * k));
-    }
-    __syncthreads();
     const unsigned long long off = (first_sample[f] + i0) * (unsigned long long)stride;
     const uint32_t total = n * stride;
     if (off + total > pcm_cap) return;
     uint8_t *dst = pcm + off;
-    if (((uintptr_t)dst & 3u) == 0) {
+    const ST *planes = work + (size_t)f * sp.channels * plane_stride(sp.max_block);
+    if (sizeof(ST) == 4 && sp.channels == 2u) {
+        // stereo of up to 24 bits (the common case): 32-bit arithmetic (a side sample has 25 bits, 2 mid + 1 has 26),
+        // 8- and 16-bit samples go straight to the stream, 24-bit ones as three half-words through shared memory
+        uint32_t lw = 0, rw = 0;
+        if (t < n) {
+            int32_t a = (int32_t)((uint32_t)(int32_t)planes[i0 + t] << r.wasted[0]);
+            int32_t b = (int32_t)((uint32_t)(int32_t)planes[plane_stride(sp.max_block) + i0 + t] << r.wasted[1]);
+            if (r.ch_code == 8u) {
+                b = a - b;
+            } else if (r.ch_code == 9u) {
+                a = a + b;
+            } else if (r.ch_code == 10u) {
+                const int32_t mid = (int32_t)((uint32_t)a << 1) | (b & 1);
+                a = (mid + b) >> 1;
+                b = (mid - b) >> 1;
+            }
+            const int32_t lo = -(1 << (sp.bits - 1u)), hi = (1 << (sp.bits - 1u)) - 1;
+            if (a < lo || a > hi || b < lo || b > hi) rec[f].status = kErrRange;  // benign race: every writer stores the same value
+            lw = (uint32_t)a;
+            rw = (uint32_t)b;
+        }
+        if (bytes == 2u) {
+            if (t < n) reinterpret_cast<uint32_t *>(dst)[t] = (lw & 0xffffu) | (rw << 16);  // off is a multiple of four
+            return;
+        }
+        if (bytes == 1u) {
+            if (t < n) reinterpret_cast<uint16_t *>(dst)[t] = (uint16_t)((lw & 0xffu) | ((rw & 0xffu) << 8));
+            return;
+        }
+        if (t < n) {
+            uint16_t *h = reinterpret_cast<uint16_t *>(stage) + 3u * t;
+            h[0] = (uint16_t)lw;
+            h[1] = (uint16_t)(((lw >> 16) & 0xffu) | ((rw & 0xffu) << 8));
+            h[2] = (uint16_t)(rw >> 8);
+        }
+    } else if (t < n) {
+        long long v[8];
+        if (!restore_sample<ST>(planes, sp.max_block, i0 + t, r, sp.channels, sp.bits, v))
+            rec[f].status = kErrRange;
+        for (uint32_t c = 0; c < sp.channels; c++)
+            for (uint32_t k = 0; k < bytes; k++) stage[t * stride + c * bytes + k] = (uint8_t)((unsigned long long)v[c] >> (8u * k));
+    }
+    __syncthreads();
+    if (((uintptr_t)dst & 15u) == 0) {
+        const uint32_t quads = total >> 4;
+        const uint4 *sq = reinterpret_cast<const uint4 *>(stage);
+        uint4 *dq = reinterpret_cast<uint4 *>(dst);
+        for (uint32_t k = t; k < quads; k += 256u) dq[k] = sq[k];
+        for (uint32_t k = (quads << 4) + t; k < total; k += 256u) dst[k] = stage[k];
+    } else if (((uintptr_t)dst & 3u) == 0) {
         const uint32_t words = total >> 2;
         const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
         uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
