@@ -446,6 +446,7 @@ def main():
                     dgot, dinfo2 = dec.decode(h_flac.numpy(), out=h_dec.numpy())
                 host_s = (time.perf_counter() - t0) / dsteps
             decode = {"value": round(nsamples * CHANNELS / dev_s / 1e6, 2), "unit": UNIT, "ms_per_stream": round(dev_s * 1e3, 3),
+                      "algorithmic_gbs": round((int(stream_bytes.size) + pcm_bytes) / dev_s / 1e9, 1),
                       "kernel_ms": round(dinfo["kernel_ms"], 3), "launches": dinfo["launches"], "frames": dinfo["n_frames"],
                       "e2e": {"value": round(nsamples * CHANNELS / host_s / 1e6, 2), "unit": UNIT, "ms_per_stream": round(host_s * 1e3, 3),
                               "h2d_bytes": int(stream_bytes.size), "d2h_bytes": pcm_bytes},
@@ -533,6 +534,19 @@ def main():
                 "all_cores": {"value": round(n * CHANNELS / dtn / 1e6, 2), "cores": cores},
             }
             line["parity"]["gpu_equals_oracle_on_sample"] = bool(nb <= got.size and (got[:nb] == ref).all())
+            if isinstance(decode, dict) and "error" not in decode:
+                # the independent CPU decoder of the test suite on the first 20 s of the same stream, one core (a
+                # deliberately plain implementation -- bit-serial CRCs -- so a reported baseline, not a target)
+                dk = min(int(ref_sizes.size), rate * 20 // BLOCK)
+                dn = dk * BLOCK
+                dbytes = int(ref_sizes[:dk].sum())
+                dstream = oracle_lib.wrap_frames(ref[:dbytes], CHANNELS, bits, rate, BLOCK, dn)
+                t0 = time.perf_counter()
+                dres = oracle_lib.decode(dstream)
+                ddt = time.perf_counter() - t0
+                decode["cpu_baseline"] = {"value": round(dn * CHANNELS / ddt / 1e6, 2), "unit": UNIT, "cores": 1, "kind": "port",
+                                          "ok": dres["rc"] == 0,
+                                          "sample": f"first {dk} frames, independent CPU decoder of the test suite (plain, bit-serial CRCs)"}
         print(json.dumps(line), flush=True)
     enc.close()
     enc2.close()

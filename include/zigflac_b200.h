@@ -61,7 +61,11 @@ typedef struct zf_config {
     uint8_t bit_depth;             /* 8, 16, 24 or 32; PCM is bit_depth/8 bytes per sample, little-endian, signed (8-bit
                                       too: see zf_wav8_to_samples) */
     uint8_t channels;              /* 1..8; 2 + stereo_decorrelation selects L/R, L/S, S/R, M/S per frame */
-    uint32_t sample_rate;          /* FrameInfo.sample_rate */
+    uint32_t sample_rate;          /* FrameInfo.sample_rate.  Rates without a frame-header code of their own (anything but 8, 16,
+                                      22.05, 24, 32, 44.1, 48, 88.2, 96, 176.4, 192 kHz) are encoded the way the reference does:
+                                      it writes the BLOCK SIZE into the rate trailer (frame_writer.zig:258-262), so
+                                      such streams are bug-compatible with upstream and decode only with decoders that take the
+                                      rate from STREAMINFO (the one below does) */
     uint8_t stereo_decorrelation;  /* Feature.stereo_decorrelation */
     uint8_t max_rice_order;        /* Feature.max_rice_order, 0..8 */
     uint8_t max_rice_param;        /* Feature.max_rice_param, 1..30 */

@@ -360,8 +360,9 @@ def _random_stream(rng, n, channels, bits):
 def test_random_configurations(zf, oracle):
     """Randomised sweep over what Encoder.Config can express (encoder.zig:609-656): block size, channels, depth, Rice
     limits, decorrelation, sample rate, stream length (any tail), first frame number -- every stream byte-identical to
-    the oracle.  Seeded: a failure prints its case."""
+    the oracle, and decoded by the device decoder back to the PCM that went in.  Seeded: a failure prints its case."""
     rng = np.random.default_rng(20250)
+    dec_handle = zf.Decoder()
     for case in range(160):
         bits = int(rng.choice([16, 24, 32]))
         channels = int(rng.choice([1, 2, 2, 2, 3, 6]))
@@ -383,3 +384,6 @@ def test_random_configurations(zf, oracle):
             got, gs = enc.encode_pcm(pcm, n, first)
         assert np.array_equal(rs, gs), what
         assert ref.tobytes() == got.tobytes(), what
+        back, info = dec_handle.decode(oracle.wrap_frames(got, channels, bits, rate, block, n))
+        assert back.tobytes() == pcm.tobytes() and info["n_frames"] == gs.size, what
+    dec_handle.close()

@@ -21,4 +21,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:v3_k
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:zf_encode_stereo_kernel -c 1 -o gpurun_out/prof_${TAG}_tail python bench.py --workload c1_16bit_44k1_60s --steps 1 --warmup 3 --profile > gpurun_out/${TAG}_ncu_tail.log 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches_c1.csv python bench.py --workload c1_16bit_44k1_60s --steps 3 --warmup 3 --profile > gpurun_out/${TAG}_ncu_c1l.log 2>&1
 timeout 300 python bench.py --workload c4_16bit_44k1_60s_lpc12 --steps 30 --warmup 5 > gpurun_out/${TAG}_bench_c4.json 2>&1; tail -c 300 gpurun_out/${TAG}_bench_c4.json
+timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:zf_dec -c 8 --csv --log-file gpurun_out/${TAG}_launches_decode.csv python tools/decode_probe.py c2 1 > gpurun_out/${TAG}_ncu_decl.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:zf_dec_frames -c 1 -o gpurun_out/prof_${TAG}_decode python tools/decode_probe.py c2 1 > gpurun_out/${TAG}_ncu_decode.log 2>&1
+for c in c1 c2 c3; do timeout 300 python tools/decode_probe.py $c 3 2>&1 | tail -2 | head -1; done > gpurun_out/${TAG}_decode_probe.txt; cat gpurun_out/${TAG}_decode_probe.txt
 tail -2 gpurun_out/${TAG}_ncu_c3.log

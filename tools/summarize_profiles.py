@@ -54,3 +54,14 @@ for key, (wl, arg) in WL.items():
     caps.append(r)
 if caps:
     json.dump({"captures": caps}, open(f'profiles/{out}_roofline.json', 'w'), indent=1)
+# decoder: launch list, one full capture of the frames kernel, the probe's timings
+for src, dst in [(f'gpurun_out/{tag}_launches_decode.csv', f'profiles/{out}_ncu_launches_decode.csv'),
+                 (f'gpurun_out/{tag}_decode_probe.txt', f'profiles/{out}_decode_probe.txt'),
+                 (f'gpurun_out/{tag}_pytest.log', f'profiles/{out}_pytest_gpu.log')]:
+    if os.path.exists(src):
+        shutil.copy(src, dst)
+rep = f'gpurun_out/prof_{tag}_decode.ncu-rep'
+if os.path.exists(rep):
+    r = summarize(rep, f'profiles/{out}_ncu_full_summary_decode.csv',
+                  'ncu --set full --clock-control none --import-source on -k regex:zf_dec_frames -c 1, python tools/decode_probe.py c2 1')
+    print('decode', r)
