@@ -384,6 +384,8 @@ def test_random_configurations(zf, oracle):
             got, gs = enc.encode_pcm(pcm, n, first)
         assert np.array_equal(rs, gs), what
         assert ref.tobytes() == got.tobytes(), what
-        back, info = dec_handle.decode(oracle.wrap_frames(got, channels, bits, rate, block, n))
-        assert back.tobytes() == pcm.tobytes() and info["n_frames"] == gs.size, what
+        if rate >= 256:  # below 256 Hz upstream's header writer ORs block-size bits into the frame-number byte:
+                         # byte-identical to the reference, but not a FLAC stream any decoder could walk
+            back, info = dec_handle.decode(oracle.wrap_frames(got, channels, bits, rate, block, n))
+            assert back.tobytes() == pcm.tobytes() and info["n_frames"] == gs.size, what
     dec_handle.close()
