@@ -161,3 +161,37 @@ def test_decoder_logic_rejects_damage(emu, oracle):
         assert ref["rc"] != 0
     n, _, _, why = emu_decode(emu, flac[:-5])  # truncated last frame
     assert n == -34
+
+
+def test_decoder_logic_fuzz(emu, oracle):
+    """Mutated and truncated streams: the decoder must come back (no endless parse), must never report success with
+    samples other than the independent decoder's, and mostly must report the damage."""
+    rng = np.random.default_rng(99)
+    t = np.arange(3 * 1024 + 200)
+    L = (5000 * np.sin(t * 0.05)).astype(np.int64) + rng.integers(-30, 31, t.size)
+    pcm = oracle.pcm_bytes_from_int(signals.interleave([L, L // 2 + 7]), 16)
+    frames, _ = oracle.encode_pcm(pcm, t.size, oracle.config(2, 16, block_size=1024), 44100)
+    flac = oracle.wrap_frames(frames, 2, 16, 44100, 1024, t.size)
+    assert emu_decode(emu, flac)[0] == pcm.size
+    reported = 0
+    for trial in range(300):
+        bad = bytearray(flac)
+        kind = trial % 3
+        if kind == 0:  # a burst of random bytes
+            at = int(rng.integers(42, len(bad) - 8))
+            for k in range(int(rng.integers(1, 9))):
+                bad[at + k] = int(rng.integers(0, 256))
+        elif kind == 1:  # zeros (endless unary runs) or ones
+            at = int(rng.integers(42, len(bad) - 64))
+            fill = 0 if trial % 2 else 0xFF
+            for k in range(int(rng.integers(8, 64))):
+                bad[at + k] = fill
+        else:  # truncation
+            bad = bad[:int(rng.integers(43, len(bad)))]
+        n, got, info, why = emu_decode(emu, bytes(bad))
+        ref = oracle.decode(bytes(bad))
+        if n >= 0 and bytes(bad) != flac:
+            assert ref["rc"] == 0 and oracle.pcm_bytes_from_int(ref["pcm"], 16).tobytes() == got.tobytes(), (trial, n)
+        else:
+            reported += 1
+    assert reported > 250

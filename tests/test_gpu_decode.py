@@ -154,6 +154,21 @@ def test_decode_header_images_and_damage(zf, oracle, dec):
         with pytest.raises(zf.FlacGpuError) as e:
             dec.decode(bytes(bad))
         assert e.value.status in (-34, -35, -33), (pos, e.value.status)
+    for trial in range(45):  # bursts of zeros / ones (endless unary runs), random bytes, truncation: reported, and the device survives
+        bad = bytearray(flac)
+        at = int(rng.integers(80, len(bad) - 200))
+        if trial % 3 == 0:
+            bad[at:at + 150] = bytes(150) if trial % 2 else bytes([255]) * 150
+        elif trial % 3 == 1:
+            bad[at:at + 6] = bytes(int(v) for v in rng.integers(0, 256, 6))
+        else:
+            bad = bad[:at]
+        ref = oracle.decode(bytes(bad))
+        try:
+            got, _ = dec.decode(bytes(bad))
+            assert ref["rc"] == 0 and oracle.pcm_bytes_from_int(ref["pcm"], 16).tobytes() == got.tobytes(), trial
+        except zf.FlacGpuError as err:
+            assert err.status in (-33, -34, -35), (trial, err.status)
     with pytest.raises(zf.FlacGpuError) as e:
         dec.decode(flac[:-5])
     assert e.value.status == -34 and e.value.info["bad_frame"] == 3
