@@ -1084,6 +1084,10 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         // piece of code, four inter-channel samples per trip (the first trip runs the chains over the history only),
         // all four candidate channels L, R, M = (L + R) >> 1, S = L - R side by side.
         bool wide_frame = false;  // 32-bit PCM only: this frame needs the 64-bit paths
+        // 16/24-bit PCM: this thread's sum |delta^k x| of every candidate -- they ARE the finest partitions' abs-sums of
+        // rice.calcSums for whichever order is chosen (a thread's sixteen samples are one finest partition), so pass 2 need
+        // not add them up again
+        uint32_t ks[WIDE ? 1 : 4][WIDE ? 1 : 5];
 #pragma unroll 1
         for (;;) {
         if constexpr (WIDE) {
@@ -1158,6 +1162,10 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
     }
             ZF3_RED(c0, 0) ZF3_RED(c1, 1) ZF3_RED(c2, 2) ZF3_RED(c3, 3)
 #undef ZF3_RED
+            ks[0][0] = c0.s0; ks[0][1] = c0.s1; ks[0][2] = c0.s2; ks[0][3] = c0.s3; ks[0][4] = c0.s4;
+            ks[1][0] = c1.s0; ks[1][1] = c1.s1; ks[1][2] = c1.s2; ks[1][3] = c1.s3; ks[1][4] = c1.s4;
+            ks[2][0] = c2.s0; ks[2][1] = c2.s1; ks[2][2] = c2.s2; ks[2][3] = c2.s3; ks[2][4] = c2.s4;
+            ks[3][0] = c3.s0; ks[3][1] = c3.s1; ks[3][2] = c3.s2; ks[3][3] = c3.s3; ks[3][4] = c3.s4;
         }
         __syncthreads();
         if (!wide_frame) {
@@ -1267,6 +1275,14 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
         }  // pass 1 + decide
         bool use_wide = false;
         if constexpr (WIDE) use_wide = wide_frame;
+        uint32_t lsum[4] = {0, 0, 0, 0};  // the leaf abs-sum of every candidate at its chosen order
+        if constexpr (!WIDE) {
+#pragma unroll
+            for (int s4 = 0; s4 < 4; s4++) {
+                const uint32_t o = sm.dec[s4].order;
+                lsum[s4] = o == 0 ? ks[s4][0] : o == 1 ? ks[s4][1] : o == 2 ? ks[s4][2] : o == 3 ? ks[s4][3] : ks[s4][4];
+            }
+        }
 #ifdef ZF_HOST_EMU
         if (t == 0) (use_wide ? g_emu_wide_frames : g_emu_narrow_frames)++;  // test harness: which path a frame took
 #endif
@@ -1284,6 +1300,19 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             int32_t r = X[kH + j];                                                                  \
             if (j < 4) r = ((uint32_t)j >= jstart) ? r : 0;                                         \
             SUM += uabs(r);                                                                         \
+            MN = r < MN ? r : MN;                                                                   \
+            MX = r > MX ? r : MX;                                                                   \
+        }                                                                                           \
+    }
+// the same without the abs-sum (16/24-bit PCM: pass 1 has it)
+#define ZF3_LEAF_MM(SLOT, X, MN, MX)                                                                \
+    {                                                                                               \
+        const uint32_t order = sm.dec[SLOT].order;                                                  \
+        diff_in_place(X, order);                                                                    \
+        const uint32_t jstart = (t == 0) ? order : 0u;                                              \
+        _Pragma("unroll") for (int j = 0; j < kS; j++) {                                            \
+            int32_t r = X[kH + j];                                                                  \
+            if (j < 4) r = ((uint32_t)j >= jstart) ? r : 0;                                         \
             MN = r < MN ? r : MN;                                                                   \
             MX = r > MX ? r : MX;                                                                   \
         }                                                                                           \
@@ -1343,8 +1372,15 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 const bool fix_a = sm.dec[slot_a].kind == kFixed, fix_b = sm.dec[slot_b].kind == kFixed;
                 typename Arith<BYTES>::U sum_a = 0, sum_b = 0;  // sixteen residuals below 2^31 each with 32-bit PCM
                 int32_t mn_a = 0, mx_a = 0, mn_b = 0, mx_b = 0;
-                if (fix_a) ZF3_LEAF(slot_a, A, sum_a, mn_a, mx_a)
-                if (fix_b) ZF3_LEAF(slot_b, B, sum_b, mn_b, mx_b)
+                if constexpr (WIDE) {
+                    if (fix_a) ZF3_LEAF(slot_a, A, sum_a, mn_a, mx_a)
+                    if (fix_b) ZF3_LEAF(slot_b, B, sum_b, mn_b, mx_b)
+                } else {
+                    if (fix_a) ZF3_LEAF_MM(slot_a, A, mn_a, mx_a)
+                    if (fix_b) ZF3_LEAF_MM(slot_b, B, mn_b, mx_b)
+                    sum_a = it ? lsum[0] : lsum[3];
+                    sum_b = it ? lsum[1] : lsum[2];
+                }
                 // width, leaf parameter, tree levels 7..3 of both candidates (FIXED or not: what the others yield is never
                 // looked at), interleaved: the chains are long and dependent
 #pragma unroll
@@ -1376,6 +1412,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
                 }
             }
 #undef ZF3_LEAF
+#undef ZF3_LEAF_MM
         }
         // round 2 of the look-back, if round 1 did not reach a prefix: its window has arrived during pass 2
         if (P.valid && warp == kW - 1 && !sm.lb_done) lb_step(sm, lba, lane, P);
