@@ -40,7 +40,7 @@ using zf::dec::StreamParams;
 
 constexpr int kSlots = 2;
 constexpr size_t kWorkBytesPerSlot = 512ull << 20;
-constexpr uint32_t kMaxBatchFrames = 16384;  // grid.y of the output kernel
+constexpr uint32_t kMaxBatchFrames = 65536;
 
 struct DSlot {
     cudaStream_t stream = nullptr;
@@ -72,6 +72,7 @@ int grow(T *&p, size_t &cap, size_t need) {
 struct zf_decoder {
     int device = 0;
     int sm_count = 148;
+    zf::dec::CrcPowers crc_pows;  // x^(8 * 2^i) mod x^16 + x^15 + x^2 + 1
     uint32_t warps_per_sm = 12;  // frames kernel: warps per SM before the lanes of a warp are filled (ZF_DEC_WARPS_PER_SM)
     cudaStream_t stream = nullptr;  // upload, scan, tables
     cudaEvent_t ev_ready = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
@@ -138,9 +139,8 @@ void launch_batch(zf_decoder *d, DSlot &sl, uint32_t first, uint32_t nb, const S
     while (lpw < 32u && (nb + lpw - 1u) / lpw > (uint32_t)d->sm_count * d->warps_per_sm) lpw *= 2u;
     zf::dec::zf_dec_frames_kernel<ST><<<(nb + lpw - 1u) / lpw, 32, 0, sl.stream>>>(d->d_stream, d->d_fpos + first, nb, lpw, sp,
                                                                                  static_cast<ST *>(sl.d_work), d->d_rec + first);
-    zf::dec::zf_dec_crc16_kernel<<<nb, 64, 0, sl.stream>>>(d->d_stream, d->d_fpos + first, nb, d->d_rec + first);
-    const dim3 grid((sp.max_block + 255u) / 256u, nb);
-    zf::dec::zf_dec_output_kernel<ST><<<grid, 256, 0, sl.stream>>>(static_cast<const ST *>(sl.d_work), d->d_rec + first,
+    zf::dec::zf_dec_crc16_kernel<<<(nb + 3u) / 4u, 128, 0, sl.stream>>>(d->d_stream, d->d_fpos + first, nb, d->crc_pows, d->d_rec + first);
+    zf::dec::zf_dec_output_kernel<ST><<<nb, 256, 0, sl.stream>>>(static_cast<const ST *>(sl.d_work), d->d_rec + first,
                                                                    d->d_first + first, sp, pcm_base, pcm_cap);
 }
 
@@ -366,6 +366,21 @@ int zf_decoder_create(int device_id, zf_decoder **out) {
     if (!d) return ZF_ERR_NOMEM;
     d->device = device_id;
     cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device_id);
+    {
+        auto mulmod = [](uint32_t a, uint32_t b) {
+            uint32_t r = 0;
+            for (int i = 15; i >= 0; i--) {
+                r = (r & 0x8000u) ? ((r << 1) ^ 0x8005u) & 0xffffu : (r << 1);
+                if ((b >> i) & 1u) r ^= a;
+            }
+            return r;
+        };
+        uint32_t v = 0x100u;  // x^8
+        for (int i = 0; i < 32; i++) {
+            d->crc_pows.pw[i] = (uint16_t)v;
+            v = mulmod(v, v);
+        }
+    }
     if (const char *e = getenv("ZF_DEC_WARPS_PER_SM")) {
         const int v = atoi(e);
         if (v >= 1 && v <= 64) d->warps_per_sm = (uint32_t)v;

@@ -532,105 +532,118 @@ __global__ void __launch_bounds__(32) zf_dec_frames_kernel(const uint8_t *s, con
     rec[f] = r;
 }
 
-// one CTA (64 threads) per frame
-__global__ void __launch_bounds__(64) zf_dec_crc16_kernel(const uint8_t *s, const unsigned long long *fpos, uint32_t n_frames,
-                                                          FrameRec *rec) {
+// x^(8 * 2^i) mod P, i < 32: computed by the host once (zf_decode.cu), passed by value
+struct CrcPowers {
+    uint16_t pw[32];
+};
+
+// One WARP per frame (four frames per CTA share the tables): the frame is cut into 32 chunks of equal length -- it is
+// thought of as padded IN FRONT with zero bytes, which do not change a CRC with zero init -- one per lane, four bytes per
+// step; the 32 chunk CRCs are then folded by a shuffle tree: CRC(A || B) = CRC(A) x^(8 |B|) + CRC(B), and at level j
+// every B is 2^j chunks long, so one multiplier serves the whole level.
+__global__ void __launch_bounds__(128) zf_dec_crc16_kernel(const uint8_t *s, const unsigned long long *fpos, uint32_t n_frames,
+                                                           CrcPowers pows, FrameRec *rec) {
     __shared__ uint16_t tab[4][256];
-    __shared__ uint32_t part[64];
-    const uint32_t f = blockIdx.x, t = threadIdx.x;
-    for (uint32_t b = t; b < 256u; b += 64u) crc16_build_tables(tab, b);
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t f = blockIdx.x * 4u + (t >> 5);
+    for (uint32_t b = t; b < 256u; b += 128u) crc16_build_tables(tab, b);
     __syncthreads();
+    if (f >= n_frames) return;
     const unsigned long long begin = fpos[f], n = fpos[f + 1] - begin;
-    const unsigned long long chunk = (n + 63ull) / 64ull;
-    const unsigned long long lo = chunk * t < n ? chunk * t : n, hi = lo + chunk < n ? lo + chunk : n;
-    part[t] = crc16_span(s + begin + lo, hi - lo, tab);
-    __syncthreads();
-    if (t == 0) {
-        const uint32_t xc = crc16_xpow8(chunk);
-        uint32_t c = 0;
-        unsigned long long done = 0;
-        for (uint32_t k = 0; k < 64u && done < n; k++) {
-            const unsigned long long m = n - done < chunk ? n - done : chunk;
-            c = crc16_mulmod(c, m == chunk ? xc : crc16_xpow8(m)) ^ part[k];
-            done += m;
-        }
-        if (c != 0 && rec[f].status == kOk) rec[f].status = kErrCrc16;
+    const unsigned long long chunk = (n + 31ull) / 32ull, pad = chunk * 32ull - n;
+    const unsigned long long lo_v = chunk * lane, hi_v = lo_v + chunk;
+    const unsigned long long lo = lo_v > pad ? lo_v - pad : 0ull, hi = hi_v > pad ? hi_v - pad : 0ull;
+    uint32_t c = crc16_span(s + begin + lo, hi - lo, tab);
+    uint32_t x = 1;  // x^(8 chunk)
+    for (uint32_t i = 0; i < 32u; i++)
+        if ((chunk >> i) & 1ull) x = crc16_mulmod(x, pows.pw[i]);
+#pragma unroll
+    for (uint32_t j = 0; j < 5u; j++) {
+        const uint32_t other = __shfl_down_sync(0xffffffffu, c, 1u << j);
+        if ((lane & ((2u << j) - 1u)) == 0u) c = crc16_mulmod(c, x) ^ other;
+        x = crc16_mulmod(x, x);
     }
+    if (lane == 0 && c != 0 && rec[f].status == kOk) rec[f].status = kErrCrc16;
 }
 
-// one CTA (256 threads) per 256 samples of a frame: restore, range check, pack little-endian, store coalesced
+// one CTA (256 threads) per frame, 256 samples per trip: restore, range check, pack little-endian, store coalesced
 template <typename ST>
 __global__ void __launch_bounds__(256) zf_dec_output_kernel(const ST *work, FrameRec *rec, const unsigned long long *first_sample,
                                                             StreamParams sp, uint8_t *pcm, unsigned long long pcm_cap) {
     __shared__ __align__(16) uint8_t stage[256 * 8 * 4];
-    const uint32_t f = blockIdx.y, i0 = blockIdx.x * 256u, t = threadIdx.x;
+    const uint32_t f = blockIdx.x, t = threadIdx.x;
     const FrameRec r = rec[f];
-    if (r.status != kOk || i0 >= r.block_size) return;
-    const uint32_t bytes = sp.bits / 8u, stride = sp.channels * bytes;
-    const uint32_t n = r.block_size - i0 < 256u ? r.block_size - i0 : 256u;
-    const unsigned long long off = (first_sample[f] + i0) * (unsigned long long)stride;
-    const uint32_t total = n * stride;
-    if (off + total > pcm_cap) return;
-    uint8_t *dst = pcm + off;
-    const ST *planes = work + (size_t)f * sp.channels * plane_stride(sp.max_block);
-    if (sizeof(ST) == 4 && sp.channels == 2u) {
-        // stereo of up to 24 bits (the common case): 32-bit arithmetic (a side sample has 25 bits, 2 mid + 1 has 26),
-        // 8- and 16-bit samples go straight to the stream, 24-bit ones as three half-words through shared memory
-        uint32_t lw = 0, rw = 0;
-        if (t < n) {
-            int32_t a = (int32_t)((uint32_t)(int32_t)planes[i0 + t] << r.wasted[0]);
-            int32_t b = (int32_t)((uint32_t)(int32_t)planes[plane_stride(sp.max_block) + i0 + t] << r.wasted[1]);
-            if (r.ch_code == 8u) {
-                b = a - b;
-            } else if (r.ch_code == 9u) {
-                a = a + b;
-            } else if (r.ch_code == 10u) {
-                const int32_t mid = (int32_t)((uint32_t)a << 1) | (b & 1);
-                a = (mid + b) >> 1;
-                b = (mid - b) >> 1;
+    if (r.status != kOk) return;
+    const uint32_t bytes = sp.bits / 8u, stride = sp.channels * bytes, pstride = plane_stride(sp.max_block);
+    const ST *planes = work + (size_t)f * sp.channels * pstride;
+    const unsigned long long off0 = first_sample[f] * (unsigned long long)stride;
+    if (off0 + (unsigned long long)r.block_size * stride > pcm_cap) return;
+    const bool stereo32 = sizeof(ST) == 4 && sp.channels == 2u;
+    const int32_t lo = (int32_t)(0xffffffffu << ((sp.bits - 1u) & 31u)), hi = ~lo;  // -2^(bits-1) .. 2^(bits-1) - 1
+    bool bad = false;
+    for (uint32_t i0 = 0; i0 < r.block_size; i0 += 256u) {
+        const uint32_t n = r.block_size - i0 < 256u ? r.block_size - i0 : 256u;
+        uint8_t *dst = pcm + off0 + (unsigned long long)i0 * stride;
+        const uint32_t total = n * stride;
+        if (stereo32) {
+            // stereo of up to 24 bits (the common case): 32-bit arithmetic (a side sample has 25 bits, 2 mid + 1 has 26),
+            // 8- and 16-bit samples go straight to the stream, 24-bit ones as three half-words through shared memory
+            uint32_t lw = 0, rw = 0;
+            if (t < n) {
+                int32_t a = (int32_t)((uint32_t)(int32_t)planes[i0 + t] << r.wasted[0]);
+                int32_t b = (int32_t)((uint32_t)(int32_t)planes[pstride + i0 + t] << r.wasted[1]);
+                if (r.ch_code == 8u) {
+                    b = a - b;
+                } else if (r.ch_code == 9u) {
+                    a = a + b;
+                } else if (r.ch_code == 10u) {
+                    const int32_t mid = (int32_t)((uint32_t)a << 1) | (b & 1);
+                    a = (mid + b) >> 1;
+                    b = (mid - b) >> 1;
+                }
+                bad = bad || a < lo || a > hi || b < lo || b > hi;
+                lw = (uint32_t)a;
+                rw = (uint32_t)b;
             }
-            const int32_t lo = -(1 << (sp.bits - 1u)), hi = (1 << (sp.bits - 1u)) - 1;
-            if (a < lo || a > hi || b < lo || b > hi) rec[f].status = kErrRange;  // benign race: every writer stores the same value
-            lw = (uint32_t)a;
-            rw = (uint32_t)b;
+            if (bytes == 2u) {
+                if (t < n) reinterpret_cast<uint32_t *>(dst)[t] = (lw & 0xffffu) | (rw << 16);  // a multiple of four bytes in
+                continue;
+            }
+            if (bytes == 1u) {
+                if (t < n) reinterpret_cast<uint16_t *>(dst)[t] = (uint16_t)((lw & 0xffu) | ((rw & 0xffu) << 8));
+                continue;
+            }
+            if (t < n) {
+                uint16_t *h = reinterpret_cast<uint16_t *>(stage) + 3u * t;
+                h[0] = (uint16_t)lw;
+                h[1] = (uint16_t)(((lw >> 16) & 0xffu) | ((rw & 0xffu) << 8));
+                h[2] = (uint16_t)(rw >> 8);
+            }
+        } else if (t < n) {
+            long long v[8];
+            if (!restore_sample<ST>(planes, sp.max_block, i0 + t, r, sp.channels, sp.bits, v)) bad = true;
+            for (uint32_t c = 0; c < sp.channels; c++)
+                for (uint32_t k = 0; k < bytes; k++) stage[t * stride + c * bytes + k] = (uint8_t)((unsigned long long)v[c] >> (8u * k));
         }
-        if (bytes == 2u) {
-            if (t < n) reinterpret_cast<uint32_t *>(dst)[t] = (lw & 0xffffu) | (rw << 16);  // off is a multiple of four
-            return;
+        __syncthreads();
+        if (((uintptr_t)dst & 15u) == 0) {
+            const uint32_t quads = total >> 4;
+            const uint4 *sq = reinterpret_cast<const uint4 *>(stage);
+            uint4 *dq = reinterpret_cast<uint4 *>(dst);
+            for (uint32_t k = t; k < quads; k += 256u) dq[k] = sq[k];
+            for (uint32_t k = (quads << 4) + t; k < total; k += 256u) dst[k] = stage[k];
+        } else if (((uintptr_t)dst & 3u) == 0) {
+            const uint32_t words = total >> 2;
+            const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
+            uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
+            for (uint32_t k = t; k < words; k += 256u) dw[k] = sw[k];
+            for (uint32_t k = (words << 2) + t; k < total; k += 256u) dst[k] = stage[k];
+        } else {
+            for (uint32_t k = t; k < total; k += 256u) dst[k] = stage[k];
         }
-        if (bytes == 1u) {
-            if (t < n) reinterpret_cast<uint16_t *>(dst)[t] = (uint16_t)((lw & 0xffu) | ((rw & 0xffu) << 8));
-            return;
-        }
-        if (t < n) {
-            uint16_t *h = reinterpret_cast<uint16_t *>(stage) + 3u * t;
-            h[0] = (uint16_t)lw;
-            h[1] = (uint16_t)(((lw >> 16) & 0xffu) | ((rw & 0xffu) << 8));
-            h[2] = (uint16_t)(rw >> 8);
-        }
-    } else if (t < n) {
-        long long v[8];
-        if (!restore_sample<ST>(planes, sp.max_block, i0 + t, r, sp.channels, sp.bits, v))
-            rec[f].status = kErrRange;
-        for (uint32_t c = 0; c < sp.channels; c++)
-            for (uint32_t k = 0; k < bytes; k++) stage[t * stride + c * bytes + k] = (uint8_t)((unsigned long long)v[c] >> (8u * k));
+        __syncthreads();  // the staging area is written again in the next trip
     }
-    __syncthreads();
-    if (((uintptr_t)dst & 15u) == 0) {
-        const uint32_t quads = total >> 4;
-        const uint4 *sq = reinterpret_cast<const uint4 *>(stage);
-        uint4 *dq = reinterpret_cast<uint4 *>(dst);
-        for (uint32_t k = t; k < quads; k += 256u) dq[k] = sq[k];
-        for (uint32_t k = (quads << 4) + t; k < total; k += 256u) dst[k] = stage[k];
-    } else if (((uintptr_t)dst & 3u) == 0) {
-        const uint32_t words = total >> 2;
-        const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage);
-        uint32_t *dw = reinterpret_cast<uint32_t *>(dst);
-        for (uint32_t k = t; k < words; k += 256u) dw[k] = sw[k];
-        for (uint32_t k = (words << 2) + t; k < total; k += 256u) dst[k] = stage[k];
-    } else {
-        for (uint32_t k = t; k < total; k += 256u) dst[k] = stage[k];
-    }
+    if (bad) rec[f].status = kErrRange;  // benign race: every writer stores the same value
 }
 #endif  // !ZF_HOST_EMU
 
