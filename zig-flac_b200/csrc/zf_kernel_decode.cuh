@@ -13,13 +13,13 @@
 //   zf_dec_frames_kernel   ONE THREAD PER FRAME: header, subframes, residual decoding and prediction in one flat loop
 //                          over the sample index (partition changes, escapes and LPC are short divergent branches),
 //                          samples of each channel written to a per-frame work plane in HBM; per-frame record with
-//                          the stereo assignment, wasted bits and a status.  A stream of a few thousand frames keeps
-//                          every SM busy with a handful of warps each; the kernel is bound by the latency of the
-//                          serial bit parse, not by bandwidth.
-//   zf_dec_crc16_kernel    one CTA per frame: CRC-16 over the whole frame (data + stored CRC must give 0), chunks
-//                          per thread by table, combined with x^(8 n) mod P.
-//   zf_dec_output_kernel   one CTA per 256 samples of a frame: wasted-bits shift, inter-channel restore, range check,
-//                          interleave, little-endian packing through shared memory, coalesced stores.
+//                          the stereo assignment, wasted bits and a status.  The kernel is bound by the latency of the
+//                          serial bit parse of one frame, not by bandwidth; frames are spread over warps before the
+//                          lanes of a warp are filled (every lane walks its own cache lines).
+//   zf_dec_crc16_kernel    one warp per frame: CRC-16 over the whole frame (data + stored CRC must give 0), 32 equal
+//                          chunks four bytes per step by slicing tables, folded by a shuffle tree.
+//   zf_dec_output_kernel   one CTA per frame: wasted-bits shift, inter-channel restore, range check, interleave,
+//                          little-endian packing, coalesced stores.
 //
 // The test suite's independent CPU decoder is the checker for this file (tests/test_gpu_decode.py, and
 // tests/test_decode_emu.py for the device functions compiled for the host); the two share no code.
