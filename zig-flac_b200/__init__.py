@@ -433,6 +433,38 @@ def wav_to_flac(wav_bytes, devices=None):
     return ZF_OK, out
 
 
+class FlacBuffer:
+    """The malloc'd result of zf_encode_wav_memory as a numpy view (no copy); release with close()."""
+
+    def __init__(self, ptr, nbytes):
+        self._p = ptr
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(ptr.value))[:nbytes]
+
+    def close(self):
+        if self._p is not None:
+            self.array = None
+            _lib().zf_free(self._p)
+            self._p = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def wav_to_flac_view(wav_bytes, devices=None):
+    """As wav_to_flac, without copying the result into a Python bytes object: (status, FlacBuffer or None)."""
+    a = _u8(wav_bytes)
+    p = C.c_void_p()
+    n = C.c_size_t()
+    devs = (C.c_int * len(devices))(*devices) if devices else None
+    rc = _lib().zf_encode_wav_memory(a.ctypes.data, a.size, C.byref(p), C.byref(n), devs, len(devices) if devices else 0)
+    if rc != ZF_OK:
+        return rc, None
+    return ZF_OK, FlacBuffer(p, n.value)
+
+
 class HostBuffer:
     """Page-locked host memory from zf_host_alloc as a numpy uint8 array (`.array`); release with close()."""
 

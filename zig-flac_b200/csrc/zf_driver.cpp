@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -168,8 +169,15 @@ struct Pipe {
     }
 };
 
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t want_samples, const int *devices, int n_devices) {
     std::lock_guard<std::mutex> one_call(g_cache.call);
+    const bool trace = getenv("ZF_TRACE") != nullptr;  // development aid: where the wall time of a whole-file call goes
+    const double t_begin = now_s();
+    double t_read = 0, t_hash = 0, t_enc = 0, t_write = 0, t_reader_done = 0, t_hasher_done = 0;
     const size_t ic_bytes = (size_t)fmt.channels * fmt.bytes_per_sample;
     const uint64_t want_frames = (want_samples + kFrameSize - 1) / kFrameSize;
     int one = 0;
@@ -217,7 +225,9 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
                 if (rc) { pipe.fail(rc); return; }
             }
             const uint64_t ask = std::min<uint64_t>(left, (uint64_t)chunk_frames * kFrameSize);
+            const double tr0 = now_s();
             size_t got = ask ? src.read(c.pcm, (size_t)ask * ic_bytes) : 0;
+            t_read += now_s() - tr0;
             if (got % ic_bytes) {  // StreamError.IncompleteStream, wav_reader.zig:52-53
                 std::lock_guard<std::mutex> lk(pipe.mu);
                 pipe.incomplete = true;
@@ -262,7 +272,10 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
                 pipe.cv.wait(lk, [&] { return pipe.rc != ZF_OK || (c.index == k && c.filled) || (pipe.n_chunks >= 0 && k >= pipe.n_chunks); });
                 if (pipe.rc != ZF_OK || (pipe.n_chunks >= 0 && k >= pipe.n_chunks)) return;
             }
+            const double th0 = now_s();
             zf_md5x_update(md5_ctx, ossl, c.pcm, c.bytes);
+            t_hash += now_s() - th0;
+            t_hasher_done = now_s() - t_begin;
             std::lock_guard<std::mutex> lk(pipe.mu);
             c.hashed = true;
             pipe.cv.notify_all();
@@ -286,8 +299,10 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
                     if (pipe.rc != ZF_OK || (pipe.n_chunks >= 0 && k >= pipe.n_chunks)) break;
                 }
                 uint32_t nf = 0;
+                const double te0 = now_s();
                 rc = zf_encode_pcm(enc, c.pcm, c.samples, c.first_frame, c.out, out_cap, &c.out_len, c.sizes.data(),
                                    (uint32_t)c.sizes.size(), &nf);
+                if (g == 0) t_enc += now_s() - te0;
                 if (rc) { pipe.fail(rc); break; }
                 std::lock_guard<std::mutex> lk(pipe.mu);
                 c.encoded = true;
@@ -319,7 +334,9 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
             if (pipe.rc != ZF_OK) { rc = pipe.rc; break; }
             if (pipe.n_chunks >= 0 && k >= pipe.n_chunks) break;
         }
+        const double tw0 = now_s();
         if (!sink.append(c.out, c.out_len)) { rc = ZF_ERR_IO; pipe.fail(rc); break; }
+        t_write += now_s() - tw0;
         for (uint32_t f = 0; f < c.frames; f++) zf_streaminfo_update_frame_size(&si, c.sizes[f]);  // wav2flac.zig:95
         std::lock_guard<std::mutex> lk(pipe.mu);
         c.index = -1;
@@ -327,8 +344,13 @@ int encode_stream(Source &src, Sink &sink, const zf_wav_format &fmt, uint64_t wa
         pipe.cv.notify_all();
     }
     reader.join();
+    t_reader_done = now_s() - t_begin;
     hasher.join();
     for (auto &w : workers) w.join();
+    if (trace)
+        fprintf(stderr, "zf trace: total %.1f ms | read %.1f (reader done at %.1f) | md5 %.1f (last chunk hashed at %.1f) | encode(dev0) %.1f | write %.1f | chunks of %u frames, ring %d\n",
+                (now_s() - t_begin) * 1e3, t_read * 1e3, t_reader_done * 1e3, t_hash * 1e3, t_hasher_done * 1e3, t_enc * 1e3, t_write * 1e3,
+                chunk_frames, ring_n);
     if (rc == ZF_OK && pipe.rc != ZF_OK) rc = pipe.rc;
     if (rc == ZF_OK && pipe.incomplete) rc = ZF_ERR_WAV_INCOMPLETE;
     if (rc == ZF_OK) {
