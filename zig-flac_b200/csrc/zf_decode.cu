@@ -82,6 +82,10 @@ struct zf_decoder {
     size_t cand_cap = 0;
     uint32_t *d_count = nullptr;
     uint32_t *h_count = nullptr;  // pinned
+    Cand *h_cand = nullptr;       // pinned: the scan kernel's hits
+    size_t h_cand_cap = 0;
+    unsigned long long *h_tab = nullptr;  // pinned: frame starts (n + 1), then first samples (n)
+    size_t h_tab_cap = 0;
     unsigned long long *d_fpos = nullptr, *d_first = nullptr;
     size_t fpos_cap = 0, first_cap = 0;
     FrameRec *d_rec = nullptr;
@@ -163,7 +167,7 @@ int decode_core(zf_decoder *d, const uint8_t *flac_host, const uint8_t *d_flac, 
         const int rc = metadata_status(zf::dec::parse_metadata(flac_host, len, si));
         if (rc) return rc;
     } else {
-        size_t take = std::min<size_t>(len, 1u << 20);
+        size_t take = std::min<size_t>(len, 4096);  // metadata is usually a few hundred bytes; more is fetched when it is not
         for (;;) {
             head.resize(take);
             ZFD_CUDA(cudaMemcpy(head.data(), d_flac, take, cudaMemcpyDeviceToHost));
@@ -217,7 +221,17 @@ int decode_core(zf_decoder *d, const uint8_t *flac_host, const uint8_t *d_flac, 
                                                                                        (uint32_t)cand_cap, d->d_count);
     ZFD_CUDA(cudaEventRecord(d->ev_s1, d->stream));
     local.launches = 1;
+    // the hit count and (in the same breath: one round trip) the first hits; page-locked staging kept in the handle
+    const size_t first_take = std::min<size_t>(cand_cap, 32768);
+    if (d->h_cand_cap < cand_cap) {
+        if (d->h_cand) cudaFreeHost(d->h_cand);
+        d->h_cand = nullptr;
+        d->h_cand_cap = 0;
+        ZFD_CUDA(cudaMallocHost(&d->h_cand, (cand_cap + cand_cap / 8 + 256) * sizeof(Cand)));
+        d->h_cand_cap = cand_cap + cand_cap / 8 + 256;
+    }
     ZFD_CUDA(cudaMemcpyAsync(d->h_count, d->d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+    ZFD_CUDA(cudaMemcpyAsync(d->h_cand, d->d_cand, first_take * sizeof(Cand), cudaMemcpyDeviceToHost, d->stream));
     ZFD_CUDA(cudaStreamSynchronize(d->stream));
     ZFD_CUDA(cudaGetLastError());
     const uint32_t n_cand = *d->h_count;
@@ -226,8 +240,12 @@ int decode_core(zf_decoder *d, const uint8_t *flac_host, const uint8_t *d_flac, 
         publish();
         return ZF_ERR_FLAC_FRAME;
     }
-    std::vector<Cand> cand_raw(n_cand);
-    if (n_cand) ZFD_CUDA(cudaMemcpy(cand_raw.data(), d->d_cand, n_cand * sizeof(Cand), cudaMemcpyDeviceToHost));
+    if (n_cand > first_take) {
+        ZFD_CUDA(cudaMemcpyAsync(d->h_cand + first_take, d->d_cand + first_take, (n_cand - first_take) * sizeof(Cand),
+                                 cudaMemcpyDeviceToHost, d->stream));
+        ZFD_CUDA(cudaStreamSynchronize(d->stream));
+    }
+    const Cand *cand_raw = d->h_cand;
     std::vector<zf::dec::HostCand> cand(n_cand);
     for (uint32_t i = 0; i < n_cand; i++) {
         cand[i].pos = cand_raw[i].pos;
@@ -273,10 +291,20 @@ int decode_core(zf_decoder *d, const uint8_t *flac_host, const uint8_t *d_flac, 
         grow(d->d_rec, d->rec_cap, (size_t)n_frames))
         return ZF_ERR_CUDA;
     static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "");
-    ZFD_CUDA(cudaMemcpyAsync(d->d_fpos, fpos.data(), (n_frames + 1) * 8, cudaMemcpyHostToDevice, d->stream));
-    ZFD_CUDA(cudaMemcpyAsync(d->d_first, first_sample.data(), n_frames * 8, cudaMemcpyHostToDevice, d->stream));
-    ZFD_CUDA(cudaEventRecord(d->ev_ready, d->stream));
-    ZFD_CUDA(cudaStreamSynchronize(d->stream));  // fpos / first_sample are pageable vectors
+    ZFD_CUDA(cudaStreamSynchronize(d->stream));  // (a retry: the staging below may still be in flight)
+    if (d->h_tab_cap < 2 * n_frames + 1) {
+        if (d->h_tab) cudaFreeHost(d->h_tab);
+        d->h_tab = nullptr;
+        d->h_tab_cap = 0;
+        const size_t want = 2 * (size_t)n_frames + 1 + n_frames / 4 + 256;
+        ZFD_CUDA(cudaMallocHost(&d->h_tab, want * 8));
+        d->h_tab_cap = want;
+    }
+    memcpy(d->h_tab, fpos.data(), (n_frames + 1) * 8);
+    memcpy(d->h_tab + n_frames + 1, first_sample.data(), n_frames * 8);
+    ZFD_CUDA(cudaMemcpyAsync(d->d_fpos, d->h_tab, (n_frames + 1) * 8, cudaMemcpyHostToDevice, d->stream));
+    ZFD_CUDA(cudaMemcpyAsync(d->d_first, d->h_tab + n_frames + 1, n_frames * 8, cudaMemcpyHostToDevice, d->stream));
+    ZFD_CUDA(cudaEventRecord(d->ev_ready, d->stream));  // the batches' streams wait for it; the host does not
 
     // ---- batches ----
     const bool wide = si.bits == 32;
@@ -423,6 +451,8 @@ void zf_decoder_destroy(zf_decoder *d) {
     if (d->d_cand) cudaFree(d->d_cand);
     if (d->d_count) cudaFree(d->d_count);
     if (d->h_count) cudaFreeHost(d->h_count);
+    if (d->h_cand) cudaFreeHost(d->h_cand);
+    if (d->h_tab) cudaFreeHost(d->h_tab);
     if (d->d_fpos) cudaFree(d->d_fpos);
     if (d->d_first) cudaFree(d->d_first);
     if (d->d_rec) cudaFree(d->d_rec);

@@ -64,7 +64,26 @@ struct HostCand {
 // Returns 0, -1 (no frame at the first offset), -2 (variable-blocksize stream).
 inline int chain_frames(std::vector<HostCand> &cand, uint64_t first_frame_offset, uint64_t stream_len, std::vector<uint64_t> &fpos,
                         std::vector<uint64_t> &first_sample, uint64_t &total_samples) {
-    std::sort(cand.begin(), cand.end(), [](const HostCand &a, const HostCand &b) { return a.pos < b.pos; });
+    // by position: the hits arrive in the order of the scan kernel's atomic counter.  Sorting 64-bit keys (position, index)
+    // and gathering is several times faster than sorting the records themselves.
+    if (cand.size() < (1u << 24) && (cand.empty() || cand.back().pos < (1ull << 40))) {
+        bool fits = true;
+        std::vector<uint64_t> key(cand.size());
+        for (size_t k = 0; k < cand.size(); k++) {
+            fits = fits && cand[k].pos < (1ull << 40);
+            key[k] = (cand[k].pos << 24) | k;
+        }
+        if (fits) {
+            std::sort(key.begin(), key.end());
+            std::vector<HostCand> sorted(cand.size());
+            for (size_t k = 0; k < cand.size(); k++) sorted[k] = cand[key[k] & 0xffffffu];
+            cand.swap(sorted);
+        } else {
+            std::sort(cand.begin(), cand.end(), [](const HostCand &a, const HostCand &b) { return a.pos < b.pos; });
+        }
+    } else {
+        std::sort(cand.begin(), cand.end(), [](const HostCand &a, const HostCand &b) { return a.pos < b.pos; });
+    }
     fpos.clear();
     first_sample.clear();
     total_samples = 0;
