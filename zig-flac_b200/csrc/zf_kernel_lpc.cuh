@@ -239,7 +239,7 @@ ZF_DEVICE uint32_t emit_lpc(const int32_t (&r)[kSpt], const long long *warm, con
 }
 
 template <int BYTES>
-__global__ void __launch_bounds__(kThreads, 1) zf_encode_stereo_lpc_kernel(const FrameJob job) {
+__global__ void __launch_bounds__(kThreads, 2) zf_encode_stereo_lpc_kernel(const FrameJob job) {
     static_assert(BYTES == 2 || BYTES == 3, "LPC kernel: 16- and 24-bit containers");
     extern __shared__ __align__(16) unsigned char zf_smem[];
     SmemLpc<BYTES> &sm = *reinterpret_cast<SmemLpc<BYTES> *>(zf_smem);
