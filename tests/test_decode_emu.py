@@ -195,3 +195,107 @@ def test_decoder_logic_fuzz(emu, oracle):
         else:
             reported += 1
     assert reported > 250
+
+
+def crafted_streams():
+    """(name, stream, expected interleaved samples, channels, bits): streams built by tests/flac_craft.py from the format
+    itself, with features no encoder of this repository emits."""
+    import flac_craft as fc
+    rng = np.random.default_rng(2024)
+    out = []
+
+    def integrate(res, warm, order):  # samples of a FIXED subframe from its residual
+        x = [int(v) for v in warm[:order]]
+        coef = {0: [], 1: [1], 2: [2, -1], 3: [3, -3, 1], 4: [4, -6, 4, -1]}[order]
+        for r in res:
+            x.append(int(r) + sum(c * x[-1 - j] for j, c in enumerate(coef)))
+        return x
+
+    # 1. 16-bit stereo, 4096: LPC order 20 (precision 12, shift 9) | FIXED order 3 with partition order 10, 5-bit
+    #    parameters, escaped partitions (one of width 0) in between
+    n = 4096
+    t = np.arange(n)
+    a = (6000 * np.sin(t * 0.03) + 2000 * np.sin(t * 0.41)).astype(np.int64) + rng.integers(-40, 41, n)
+    coefs = [int(v) for v in rng.integers(-300, 301, 20)]
+    params_a = [13] * 4
+    b = (3000 * np.sin(t * 0.011)).astype(np.int64) + rng.integers(-3, 4, n)
+    b[1000:1200] = 77  # a stretch of zero residuals
+    d = b.copy()
+    for _ in range(3):
+        d = np.concatenate([d[:1], d[1:] - d[:-1]])
+    res_b = d[3:]
+    psize = n >> 10
+    params_b = []
+    for p in range(1 << 10):
+        lo, hi = max(p * psize - 3, 0), (p + 1) * psize - 3
+        part = res_b[lo:hi]
+        width = max([int(v).bit_length() + 1 for v in part if v != 0] + [0])
+        if width == 0 and p % 2:
+            params_b.append(("esc", 0))
+        elif p % 50 == 7:
+            params_b.append(("esc", width))
+        else:
+            params_b.append(int(rng.integers(0, 4)) if p % 3 else 17)
+    f = fc.frame(0, n, 9, 1, 4, [lambda w: fc.subframe_lpc(w, a, 16, 20, coefs, 12, 9, 2, 0, params_a),
+                                 lambda w: fc.subframe_fixed(w, b, 16, 3, 10, 1, params_b)])
+    out.append(("lpc20_po10", fc.stream([f], 2, 16, 44100, n, n, n), signals.interleave([a, b]), 2, 16))
+
+    # 2. explicit block-size fields: three frames of 1000 (16-bit field), a last one of 200 (8-bit field); mid/side with
+    #    wasted bits on the LPC mid channel; metadata blocks full of sync patterns in front
+    frames, exp_l, exp_r = [], [], []
+    for k, bs in enumerate((1000, 1000, 1000, 200)):
+        tt = np.arange(bs) + 1000 * k
+        left = (9000 * np.sin(tt * 0.02)).astype(np.int64)
+        right = left // 2 + rng.integers(-9, 10, bs)
+        left = (left >> 3) << 3
+        right = (right >> 3) << 3  # mid and side are multiples of 4 / 8
+        mid, side = (left + right) >> 1, left - right
+        c5 = [int(v) for v in rng.integers(-200, 201, 5)]
+        frames.append(fc.frame(7 + k, bs, 10, 10, 4,
+                               [lambda w, mid=mid, c5=c5: fc.subframe_lpc(w, mid, 16, 5, c5, 10, 7, 0, 0, [12], wasted=2),
+                                lambda w, side=side: fc.subframe_fixed(w, side, 17, 1, 0, 0, [11], wasted=3)],
+                               explicit_block=16 if bs == 1000 else 8))
+        exp_l.append(left)
+        exp_r.append(right)
+    meta = [(1, bytes([0xFF, 0xF8] * 40)), (2, b"test" + bytes([0xFF, 0xF8, 0xC9, 0x18, 0x00, 0xC2] * 9))]
+    out.append(("explicit_blocks_ms", fc.stream(frames, 2, 16, 48000, 1000, 1000, 3200, meta),
+                signals.interleave([np.concatenate(exp_l), np.concatenate(exp_r)]), 2, 16))
+
+    # 3. 24-bit mono, 4096, FIXED order 1 with partition order 12: 4096 partitions of ONE sample, the first one empty
+    res = rng.integers(-3000, 3001, n - 1)
+    m = integrate(res, [123456], 1)
+    params = [int(v) for v in rng.integers(8, 13, 1 << 12)]
+    f = fc.frame(0, n, 11, 0, 6, [lambda w: fc.subframe_fixed(w, m, 24, 1, 12, 0, params)])
+    out.append(("po12_single_sample_partitions", fc.stream([f], 1, 24, 96000, n, n, n), np.array(m, dtype=np.int64), 1, 24))
+
+    # 4. LPC order 32, precision 15, shift 14, three channels (one CONSTANT, one VERBATIM)
+    n4 = 576
+    x = (20000 * np.sin(np.arange(n4) * 0.1)).astype(np.int64)
+    c32 = [int(v) for v in rng.integers(-16000, 16001, 32)]
+    v = rng.integers(-32768, 32768, n4)
+
+    def const_sub(w):
+        w.put(0, 8)
+        w.put_signed(-777, 16)
+
+    def verb_sub(w):
+        w.put(1 << 1, 8)
+        for s in v:
+            w.put_signed(int(s), 16)
+
+    f = fc.frame(3, n4, 9, 2, 4, [lambda w: fc.subframe_lpc(w, x, 16, 32, c32, 15, 14, 1, 1, [25, 24]), const_sub, verb_sub])
+    out.append(("lpc32_three_channels", fc.stream([f], 3, 16, 44100, n4, n4, n4),
+                signals.interleave([x, np.full(n4, -777), v]), 3, 16))
+    return out
+
+
+def test_decoder_logic_crafted_streams(emu, oracle):
+    """Features beyond what the repository's encoders emit, from a third statement of the format (tests/flac_craft.py):
+    the device decoder's logic and the independent CPU decoder must both return the crafted samples."""
+    for name, flac, expect, channels, bits in crafted_streams():
+        pcm = oracle.pcm_bytes_from_int(expect, bits)
+        ref = oracle.decode(flac)
+        assert ref["rc"] == 0, (name, ref["rc"])
+        assert oracle.pcm_bytes_from_int(ref["pcm"], bits).tobytes() == pcm.tobytes(), name
+        n, got, info, bad = emu_decode(emu, flac)
+        assert n == pcm.size and got.tobytes() == pcm.tobytes(), (name, n, bad)

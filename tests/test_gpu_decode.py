@@ -194,3 +194,25 @@ def test_decode_full_size_roundtrip(zf, oracle, dec, name, bits, rate, seconds):
     assert info["md5_status"] == 1 and info["n_frames"] == (n + 4095) // 4096
     assert got.size == pcm.size
     assert np.array_equal(got, pcm)
+
+
+def test_decode_crafted_streams(zf, oracle, dec):
+    """Streams built from the format by tests/flac_craft.py with features no encoder here emits: LPC orders 20 and 32,
+    partition orders 10 and 12 (single-sample partitions, an empty first partition), 5-bit parameters with escapes of
+    width 0, explicit 8- / 16-bit block-size fields, wasted bits under mid/side, CONSTANT and VERBATIM beside LPC,
+    metadata blocks full of sync patterns."""
+    from test_decode_emu import crafted_streams
+    for name, flac, expect, channels, bits in crafted_streams():
+        pcm = oracle.pcm_bytes_from_int(expect, bits)
+        got, info = dec.decode(flac)
+        assert got.tobytes() == pcm.tobytes(), name
+        assert info["channels"] == channels and info["bit_depth"] == bits, name
+    # the encoder's own empty first partition (SURVEY Q6): block 16, order 4, partition order 2
+    rng = np.random.default_rng(16)
+    for trial in range(40):
+        n = 16 * 5
+        x = np.cumsum(np.cumsum(np.cumsum(np.cumsum(rng.integers(-3, 4, n))))) % 20000 - 10000
+        pcm = oracle.pcm_bytes_from_int(signals.interleave([x, x // 2]), 16)
+        frames, _ = oracle.encode_pcm(pcm, n, oracle.config(2, 16, block_size=16), 44100)
+        got, _ = dec.decode(oracle.wrap_frames(frames, 2, 16, 44100, 16, n))
+        assert got.tobytes() == pcm.tobytes(), trial

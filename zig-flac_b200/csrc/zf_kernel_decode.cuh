@@ -321,18 +321,18 @@ ZF_DEVICE uint32_t decode_subframe(BitR &br, ST *out, ST *ring, uint32_t bs, uin
     if (psize < order) return kErrRange;
     if (br.overrun()) return kErrOverrun;
     // One flat loop over the sample index for all lanes of the warp (their partition sizes differ: a change of
-    // partition is a short divergent branch, not a loop boundary).  "A partition ends here": the first parameter is
-    // read in front of sample `order`.
-    uint32_t part_end = order, next_end = psize;
+    // partition is a short divergent branch, not a loop boundary).  part_end: end of the partition whose parameter was
+    // read last (none yet); the first partition holds psize - order samples and may be EMPTY (psize == order), in which
+    // case two parameters stand in front of the first code.
+    uint32_t part_end = 0;
     uint32_t k = 0, raw = 0;
     bool esc = false;
 #define ZF_DEC_RESIDUAL(R)                                                                       \
-    if (i == part_end) {                                                                         \
+    while (i >= part_end) {                                                                      \
         k = br.read(plen);                                                                       \
         esc = k == escape;                                                                       \
         if (esc) raw = br.read(5);                                                               \
-        part_end = next_end;                                                                     \
-        next_end += psize;                                                                       \
+        part_end += psize;                                                                       \
     }                                                                                            \
     ST R;                                                                                        \
     if (esc) {                                                                                   \
