@@ -137,8 +137,9 @@ def subframe_fixed(w, samples, bps, order, part_order, method, params, wasted=0)
     residual(w, res, len(x), order, part_order, method, params)
 
 
-def frame(number, block, rate_code, ch_code, depth_code, subframes, explicit_block=None):
-    """subframes: callables that write one subframe into the bit writer.  explicit_block: 8 or 16 forces the explicit field."""
+def frame(number, block, rate_code, ch_code, depth_code, subframes, explicit_block=None, rate_trailer=b""):
+    """subframes: callables that write one subframe into the bit writer.  explicit_block: 8 or 16 forces the explicit field;
+    rate_trailer: the bytes behind the header for rate codes 12 (one byte), 13 and 14 (two)."""
     hdr = bytearray([0xFF, 0xF8])
     if explicit_block == 8:
         bs_code = 6
@@ -154,6 +155,7 @@ def frame(number, block, rate_code, ch_code, depth_code, subframes, explicit_blo
         hdr.append(block - 1)
     elif bs_code == 7:
         hdr += bytes([(block - 1) >> 8, (block - 1) & 0xFF])
+    hdr += rate_trailer
     hdr.append(_crc8(hdr))
     w = Bits()
     for s in subframes:

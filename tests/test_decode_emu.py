@@ -286,6 +286,34 @@ def crafted_streams():
     f = fc.frame(3, n4, 9, 2, 4, [lambda w: fc.subframe_lpc(w, x, 16, 32, c32, 15, 14, 1, 1, [25, 24]), const_sub, verb_sub])
     out.append(("lpc32_three_channels", fc.stream([f], 3, 16, 44100, n4, n4, n4),
                 signals.interleave([x, np.full(n4, -777), v]), 3, 16))
+
+    # 5. 32-bit stereo left/side: a 33-bit side channel through LPC order 2 with parameters 28 / 29, long unary runs
+    #    (parameter 0, quotients far beyond 64), an escape of width 31, frame numbers with long codes, a sample-rate trailer,
+    #    the depth taken from STREAMINFO (code 0).  One stream per starting frame number.
+    n5 = 256
+    big = 1 << 31
+    i5 = np.arange(n5)
+    for k, number in enumerate((0x7F, 0x80, 0x7FF, 0x800)):
+        nz = rng.integers(0, 50, n5)
+        right = np.where(i5 % 2 == 0, -big + nz, big - 1 - nz).astype(object)          # within a hair of full scale
+        if k % 2 == 0:
+            left = np.where(i5 % 2 == 0, (1 << 30) - 1, -(1 << 30)).astype(object)     # escape of width 31, order 0
+            lsub = lambda w, left=left: fc.subframe_fixed(w, left, 32, 0, 0, 1, [("esc", 31)])
+        else:
+            q = [int(v) for v in rng.integers(0, 3, n5)]
+            q[5], q[100], q[101] = 40, 150, 33                                         # unary runs of 40, 150 and 33 zeros
+            left = np.array(integrate([(v >> 1) ^ -(v & 1) for v in q[1:]], [5], 1), dtype=object)
+            lsub = lambda w, left=left: fc.subframe_fixed(w, left, 32, 1, 0, 1, [0])   # parameter 0: the code is the run
+        side = left - right                                                            # about +-1.5 * 2^31: 33 bits
+        ssub = lambda w, side=side: fc.subframe_lpc(w, side, 33, 2, [-2, -1], 4, 0, 1, 1, [28, 29])
+        f5 = fc.frame(number, n5, 13, 8, 0, [lsub, ssub], rate_trailer=bytes([0xAC, 0x44]))
+        out.append((f"wide_side_{k}", fc.stream([f5], 2, 32, 44100, n5, n5, n5), signals.interleave([left, right]), 2, 32))
+
+    # 6. 8-bit mono with the largest partition order a block of 192 allows (6: partitions of three samples), order 2
+    n6 = 192
+    x6 = (100 * np.sin(np.arange(n6) * 0.2)).astype(np.int64)
+    f = fc.frame(2, n6, 4, 0, 1, [lambda w: fc.subframe_fixed(w, x6, 8, 2, 6, 0, [int(v) for v in rng.integers(0, 6, 64)])])
+    out.append(("8bit_192", fc.stream([f], 1, 8, 8000, n6, n6, n6), x6, 1, 8))
     return out
 
 
