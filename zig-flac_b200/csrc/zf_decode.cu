@@ -39,7 +39,7 @@ using zf::dec::FrameRec;
 using zf::dec::StreamParams;
 
 constexpr int kSlots = 2;
-constexpr size_t kWorkBytesPerSlot = 512ull << 20;
+constexpr size_t kWorkBytesPerSlot = 2048ull << 20;  // frames of one batch (their bit parse is latency-bound: fewer, larger batches are faster)
 constexpr uint32_t kMaxBatchFrames = 65536;
 
 struct DSlot {
