@@ -103,3 +103,32 @@ extern "C" long long emu_decode_flac(const uint8_t *flac, size_t len, uint8_t *p
     if (si.total_samples && si.total_samples != total) return -35;
     return (long long)need;
 }
+
+#ifdef ZF_EMU_DECODE_MAIN
+// Stand-alone form for AddressSanitizer runs (tests/test_decode_emu.py::test_decoder_logic_memory_safety): streams from
+// files named on the command line, output buffer of exactly the size STREAMINFO announces (or 1 MB), work planes and the
+// padded stream copy of exactly the sizes the product allocates -- an access outside them stops the program.
+int main(int argc, char **argv) {
+    int worst = 0;
+    for (int a = 1; a < argc; a++) {
+        FILE *f = fopen(argv[a], "rb");
+        if (!f) return 2;
+        std::vector<uint8_t> data;
+        uint8_t tmp[65536];
+        size_t got;
+        while ((got = fread(tmp, 1, sizeof tmp, f)) > 0) data.insert(data.end(), tmp, tmp + got);
+        fclose(f);
+        HostStreamInfo si;
+        memset(&si, 0, sizeof si);
+        size_t cap = 1 << 20;
+        if (parse_metadata(data.data(), data.size(), si) == 0 && si.total_samples)
+            cap = (size_t)si.total_samples * si.channels * ((si.bits + 7) / 8);
+        std::vector<uint8_t> pcm(cap ? cap : 1);
+        uint32_t info[4] = {0, 0, 0, 0}, bad[2] = {0, 0};
+        const long long rc = emu_decode_flac(data.data(), data.size(), pcm.data(), cap, info, bad);
+        printf("%s %lld\n", argv[a], rc);
+        if (rc < 0) worst = 1;
+    }
+    return worst ? 1 : 0;
+}
+#endif

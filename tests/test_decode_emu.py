@@ -327,3 +327,50 @@ def test_decoder_logic_crafted_streams(emu, oracle):
         assert oracle.pcm_bytes_from_int(ref["pcm"], bits).tobytes() == pcm.tobytes(), name
         n, got, info, bad = emu_decode(emu, flac)
         assert n == pcm.size and got.tobytes() == pcm.tobytes(), (name, n, bad)
+
+
+def test_decoder_logic_memory_safety(oracle, tmp_path):
+    """The decoder's device functions under AddressSanitizer (compute-sanitizer is not available on the GPU pool): the
+    crafted streams, and some four hundred damaged copies of them, with every buffer of exactly the size the product
+    allocates -- any access outside stops the program."""
+    exe = os.path.join(EMU_DIR, "_build", "emu_decode_asan")
+    srcs = [os.path.join(EMU_DIR, "emu_decode.cpp"), os.path.join(CSRC, "zf_kernel_decode.cuh"), os.path.join(CSRC, "zf_decode_host.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(s) > os.path.getmtime(exe) for s in srcs):
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fwrapv", "-fsanitize=address,undefined", "-fno-sanitize=shift,signed-integer-overflow",
+                            "-fno-omit-frame-pointer", "-DZF_EMU_DECODE_MAIN", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", exe,
+                            os.path.join(EMU_DIR, "emu_decode.cpp")], capture_output=True, text=True)
+        if r.returncode != 0 and "asan" in (r.stderr or "").lower():
+            pytest.skip("no AddressSanitizer runtime in this toolchain")
+        assert r.returncode == 0, r.stderr
+    rng = np.random.default_rng(7)
+    files = []
+    for name, flac, expect, channels, bits in crafted_streams():
+        p = tmp_path / f"{name}.flac"
+        p.write_bytes(flac)
+        files.append(str(p))
+        for k in range(45):
+            bad = bytearray(flac)
+            kind = k % 4
+            if kind == 0:
+                at = int(rng.integers(4, len(bad)))
+                bad[at] ^= 1 << int(rng.integers(0, 8))
+            elif kind == 1:
+                at = int(rng.integers(42, max(43, len(bad) - 40)))
+                bad[at:at + 32] = bytes(32) if k % 8 < 4 else bytes([255]) * 32
+            elif kind == 2:
+                bad = bad[:int(rng.integers(8, len(bad)))]
+            else:
+                at = int(rng.integers(42, max(43, len(bad) - 8)))
+                bad[at:at + 6] = bytes(int(v) for v in rng.integers(0, 256, 6))
+            q = tmp_path / f"{name}_{k}.flac"
+            q.write_bytes(bytes(bad))
+            files.append(str(q))
+    r = subprocess.run([exe] + files, capture_output=True, text=True, timeout=600, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
+    assert r.returncode in (0, 1), (r.returncode, r.stderr[-2000:])
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == len(files)
+    good = {l.split()[0]: int(l.split()[1]) for l in lines}
+    for name, flac, expect, channels, bits in crafted_streams():
+        assert good[str(tmp_path / f"{name}.flac")] == len(expect) * (bits // 8), name
