@@ -31,6 +31,7 @@
 #include "zf_kernel.cuh"
 
 #ifdef ZF_HOST_EMU
+#include <math.h>
 #define ZF_NOINLINE inline
 #else
 #define ZF_NOINLINE __device__ __noinline__
@@ -291,7 +292,41 @@ struct Chain {
             s0 += uabs(x); s1 += uabs(e1); s2 += uabs(e2); s3 += uabs(e3); s4 += uabs(e4);
         }
     }
+    ZF_DEVICE void take_out(uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4) { s1 -= a1; s2 -= a2; s3 -= a3; s4 -= a4; }
+    ZF_DEVICE void sums(uint32_t (&o)[5]) const { o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3; o[4] = s4; }
 };
+
+// The same in SINGLE PRECISION for 16-bit PCM.  Every quantity is an integer that a float carries exactly: samples and
+// the side channel below 2^17, fourth differences below 2^21, a thread's sixteen-term sums at most 2^24 (every partial sum
+// of non-negative integers up to 2^24 is representable).  |e| is then a free operand modifier of the accumulating FADD,
+// and the FP32 pipe is twice as wide as the integer pipe: 9 instructions per chain and sample instead of 14
+// (tools/microbench/chain_bench.cu: 14.0 against 19.0 SM-clocks per warp-sample for the four chains).
+struct ChainF {
+    float xp, e1p, e2p, e3p, s0, s1, s2, s3, s4;
+    uint32_t orv;
+    ZF_DEVICE void init() { xp = e1p = e2p = e3p = 0.0f; s0 = s1 = s2 = s3 = s4 = 0.0f; orv = 0; }
+    template <bool ACC>
+    ZF_DEVICE void step(int32_t xi) {
+        const float x = (float)xi;
+        const float e1 = x - xp, e2 = e1 - e1p, e3 = e2 - e2p, e4 = e3 - e3p;
+        xp = x; e1p = e1; e2p = e2; e3p = e3;
+        if (ACC) {
+            orv |= (uint32_t)xi;
+            s0 += fabsf(x); s1 += fabsf(e1); s2 += fabsf(e2); s3 += fabsf(e3); s4 += fabsf(e4);
+        }
+    }
+    ZF_DEVICE void take_out(uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4) {
+        s1 -= (float)a1; s2 -= (float)a2; s3 -= (float)a3; s4 -= (float)a4;
+    }
+    ZF_DEVICE void sums(uint32_t (&o)[5]) const {
+        o[0] = (uint32_t)s0; o[1] = (uint32_t)s1; o[2] = (uint32_t)s2; o[3] = (uint32_t)s3; o[4] = (uint32_t)s4;
+    }
+};
+
+template <int BYTES> struct Pass1Chain { typedef Chain type; };
+#ifndef ZF_V3_INT16_PASS1
+template <> struct Pass1Chain<2> { typedef ChainF type; };
+#endif
 
 // the same in 64 bits, with the OR of |delta^k x| that fixed.bestOrder's range check needs (fixed.zig:160-162)
 struct ChainW {
@@ -1097,7 +1132,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             else pass1_pairs<BYTES, ChainN>(sm, t, lane, warp);
         } else
         {
-            Chain c0, c1, c2, c3;
+            typename Pass1Chain<BYTES>::type c0, c1, c2, c3;
             c0.init(); c1.init(); c2.init(); c3.init();
             {
                 int32_t L[4], R[4];
@@ -1134,10 +1169,7 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
             const int32_t x = (EXPR);                                                   \
             const int32_t e1 = x - fxp, e2 = e1 - f1p, e3 = e2 - f2p, e4 = e3 - f3p;    \
             fxp = x; f1p = e1; f2p = e2; f3p = e3;                                      \
-            if (q < 1) C.s1 -= uabs(e1);                                                \
-            if (q < 2) C.s2 -= uabs(e2);                                                \
-            if (q < 3) C.s3 -= uabs(e3);                                                \
-            C.s4 -= uabs(e4);                                                           \
+            C.take_out(q < 1 ? uabs(e1) : 0u, q < 2 ? uabs(e2) : 0u, q < 3 ? uabs(e3) : 0u, uabs(e4)); \
             sm.warm[SLOT][q] = x;                                                       \
         }                                                                               \
     }
@@ -1147,8 +1179,10 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
 #define ZF3_RED(C, SLOT)                                                                         \
     {                                                                                            \
         uint32_t *rp = &sc.red[warp][SLOT][0];                                                   \
-        const uint32_t sv[5] = {C.s0, C.s1, C.s2, C.s3, C.s4};                                   \
+        uint32_t sv[5];                                                                          \
+        C.sums(sv);                                                                              \
         _Pragma("unroll") for (int k = 0; k < 5; k++) {                                          \
+            ks[SLOT][k] = sv[k];                                                                 \
             if (BYTES == 2) { /* 16 x 2^20 x 32 lanes < 2^32 */                                  \
                 const uint32_t ws = reduce_add(sv[k]);                                           \
                 if (lane == 0) { rp[2 * k] = ws; rp[2 * k + 1] = 0; }                            \
@@ -1162,10 +1196,6 @@ __global__ void __launch_bounds__(kT, CtasPerSm<BYTES>::value) zf_encode_stereo_
     }
             ZF3_RED(c0, 0) ZF3_RED(c1, 1) ZF3_RED(c2, 2) ZF3_RED(c3, 3)
 #undef ZF3_RED
-            ks[0][0] = c0.s0; ks[0][1] = c0.s1; ks[0][2] = c0.s2; ks[0][3] = c0.s3; ks[0][4] = c0.s4;
-            ks[1][0] = c1.s0; ks[1][1] = c1.s1; ks[1][2] = c1.s2; ks[1][3] = c1.s3; ks[1][4] = c1.s4;
-            ks[2][0] = c2.s0; ks[2][1] = c2.s1; ks[2][2] = c2.s2; ks[2][3] = c2.s3; ks[2][4] = c2.s4;
-            ks[3][0] = c3.s0; ks[3][1] = c3.s1; ks[3][2] = c3.s2; ks[3][3] = c3.s3; ks[3][4] = c3.s4;
         }
         __syncthreads();
         if (!wide_frame) {
